@@ -1,0 +1,272 @@
+"""CPU oracle for the MoCo contrastive hot path (TEST INFRASTRUCTURE ONLY).
+
+This file restates, in plain numpy, the algorithm of the reference's hot path
+(bl0/moco).  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import it.  The product
+(``moco_b200``) never imports anything from ``oracle/``.
+
+Parity pinning: the reference ships no tests, golden vectors or known-answer
+files.  The oracle is therefore pinned against OUTPUTS OF
+THE REFERENCE ITSELF: ``tests/golden/gen_golden.py`` imports the unmodified
+reference from ``/root/reference`` (with the CPU shims described there), runs
+it on seeded inputs and commits the results under ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` checks every function below against those
+fixtures.  The arithmetic the reference delegates to PyTorch (third-party,
+``pytorch>=1.3``, reference ``README.md:14``; 2.11.0 installed here) is restated
+from its published algorithms: ``torch.randperm`` on the CPU generator is
+MT19937 + a forward Fisher-Yates (`randperm_cpu`), ``nn.CrossEntropyLoss`` is
+mean(logsumexp - x[label]).
+
+Every function cites the reference file:line it follows (paths relative to
+``/root/reference``).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+# --------------------------------------------------------------------------
+# torch CPU generator restatement (MT19937) -- used by get_shuffle_ids
+# --------------------------------------------------------------------------
+
+
+class MT19937:
+    """32-bit Mersenne Twister, `init_genrand(seed)` seeding.
+
+    ``torch.manual_seed(s)`` seeds the CPU generator's mt19937 engine with
+    ``s`` (low 32 bits) and ``generator->random()`` returns successive 32-bit
+    outputs; this is the textbook MT19937 (Matsumoto & Nishimura 1998).
+    """
+
+    N, M = 624, 397
+
+    def __init__(self, seed: int):
+        mt = np.zeros(self.N, dtype=np.uint64)
+        mt[0] = seed & 0xFFFFFFFF
+        for i in range(1, self.N):
+            prev = int(mt[i - 1])
+            mt[i] = (1812433253 * (prev ^ (prev >> 30)) + i) & 0xFFFFFFFF
+        self.mt = mt.astype(np.uint32)
+        self.pos = self.N
+
+    def _twist(self) -> None:
+        mt = self.mt.astype(np.uint64)
+        N, M = self.N, self.M
+        # the recurrence reads already-updated words for i >= N-M, so do it in
+        # three dependent vector blocks exactly like the scalar loop would.
+        def blk(lo, hi, src_off):
+            y = (mt[lo:hi] & 0x80000000) | (mt[lo + 1:hi + 1] & 0x7FFFFFFF)
+            mag = np.where(y & 1, np.uint64(0x9908B0DF), np.uint64(0))
+            mt[lo:hi] = mt[lo + src_off:hi + src_off] ^ (y >> np.uint64(1)) ^ mag
+        blk(0, N - M, M)                     # i in [0, 227): uses mt[i+397] (old)
+        blk(N - M, 2 * (N - M), M - N)       # i in [227, 454): uses mt[i-227] (new)
+        blk(2 * (N - M), N - 1, M - N)       # i in [454, 623): uses mt[i-227] (new)
+        y = (mt[N - 1] & 0x80000000) | (mt[0] & 0x7FFFFFFF)
+        mag = np.uint64(0x9908B0DF) if (int(y) & 1) else np.uint64(0)
+        mt[N - 1] = mt[M - 1] ^ (y >> np.uint64(1)) ^ mag
+        self.mt = mt.astype(np.uint32)
+        self.pos = 0
+
+    def random_raw(self, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.uint32)
+        got = 0
+        while got < n:
+            if self.pos >= self.N:
+                self._twist()
+            take = min(n - got, self.N - self.pos)
+            y = self.mt[self.pos:self.pos + take].astype(np.uint64)
+            y ^= y >> np.uint64(11)
+            y ^= (y << np.uint64(7)) & np.uint64(0x9D2C5680)
+            y ^= (y << np.uint64(15)) & np.uint64(0xEFC60000)
+            y ^= y >> np.uint64(18)
+            out[got:got + take] = (y & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+            self.pos += take
+            got += take
+        return out
+
+
+def torch_cpu_randperm(n: int, seed: int) -> np.ndarray:
+    """``torch.manual_seed(seed); torch.randperm(n)`` on the CPU generator.
+
+    PyTorch's ``randperm_cpu`` (aten/src/ATen/native/TensorFactories.cpp):
+    ``for i in [0, n-1): z = random() % (n-i); swap(r[i], r[i+z])``.
+    Called by the reference at moco/util.py:102-104.
+    """
+    r = np.arange(n, dtype=np.int64)
+    if n <= 1:
+        return r
+    raw = MT19937(seed).random_raw(n - 1)
+    for i in range(n - 1):
+        z = int(raw[i]) % (n - i)
+        r[i], r[i + z] = r[i + z], r[i]
+    return r
+
+
+# --------------------------------------------------------------------------
+# ShuffleBN  (reference moco/util.py:47-111)
+# --------------------------------------------------------------------------
+
+
+def get_shuffle_ids(bsz: int, epoch: int) -> Tuple[np.ndarray, np.ndarray]:
+    """moco/util.py:99-111 -- forward permutation and its inverse (int64)."""
+    forward_inds = torch_cpu_randperm(bsz, epoch)
+    backward_inds = np.zeros(bsz, dtype=np.int64)
+    backward_inds[forward_inds] = np.arange(bsz, dtype=np.int64)  # index_copy_, util.py:107-109
+    return forward_inds, backward_inds
+
+
+def dist_collect(xs: Sequence[np.ndarray]) -> np.ndarray:
+    """moco/util.py:47-58 -- all_gather + cat along dim 0, rank-major."""
+    return np.concatenate([np.ascontiguousarray(x) for x in xs], axis=0)
+
+
+def get_local_id(ids: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """moco/util.py:95-97 -- ``ids.chunk(world)[rank]``."""
+    n = ids.shape[0] // world
+    return ids[rank * n:(rank + 1) * n]
+
+
+def forward_shuffle(xs: Sequence[np.ndarray], epoch: int) -> Tuple[List[np.ndarray], np.ndarray]:
+    """moco/util.py:69-79 for every rank at once.
+
+    ``xs[r]`` is rank r's local batch.  Returns (per-rank shuffled batches,
+    backward_inds).
+    """
+    world = len(xs)
+    x_all = dist_collect(xs)
+    fwd, bwd = get_shuffle_ids(x_all.shape[0], epoch)
+    outs = [x_all[get_local_id(fwd, r, world)] for r in range(world)]
+    return outs, bwd
+
+
+def backward_shuffle(xs: Sequence[np.ndarray], backward_inds: np.ndarray,
+                     return_local: bool = True):
+    """moco/util.py:81-93 for every rank at once.
+
+    Returns (x_all_unshuffled, [x_local per rank]) or x_all_unshuffled.
+    """
+    world = len(xs)
+    x_all = dist_collect(xs)
+    unshuf = x_all[backward_inds]
+    if not return_local:
+        return unshuf
+    locals_ = [x_all[get_local_id(backward_inds, r, world)] for r in range(world)]
+    return unshuf, locals_
+
+
+# --------------------------------------------------------------------------
+# MemoryMoCo + NCESoftmaxLoss  (reference moco/NCE/Contrast.py, NCECriterion.py)
+# --------------------------------------------------------------------------
+
+
+def queue_init_bound(feature_dim: int) -> float:
+    """moco/NCE/Contrast.py:16 -- stdv = 1/sqrt(feature_dim/3)."""
+    return 1.0 / math.sqrt(feature_dim / 3)
+
+
+def enqueue_ids(index: int, all_size: int, queue_size: int) -> np.ndarray:
+    """moco/NCE/Contrast.py:32 -- fmod(arange(all_size) + index, queue_size)."""
+    return np.fmod(np.arange(all_size, dtype=np.int64) + index, queue_size)
+
+
+class MemoryMoCoOracle:
+    """moco/NCE/Contrast.py:6-36 in numpy (fp32 like the reference)."""
+
+    def __init__(self, memory: np.ndarray, temperature: float = 0.07, index: int = 0):
+        self.memory = np.array(memory, dtype=np.float32, copy=True)
+        self.queue_size = self.memory.shape[0]
+        self.temperature = temperature
+        self.index = index
+
+    def logits(self, q: np.ndarray, k: np.ndarray) -> np.ndarray:
+        """Contrast.py:21-27 (no queue mutation)."""
+        q = q.astype(np.float32)
+        k = k.astype(np.float32)
+        l_pos = (q * k).sum(axis=-1, keepdims=True)                  # :23
+        l_neg = q @ self.memory.T                                     # :25 (pre-update snapshot)
+        out = np.concatenate([l_pos, l_neg], axis=1)                  # :26
+        return np.ascontiguousarray(out / np.float32(self.temperature))  # :27
+
+    def enqueue(self, k_all: np.ndarray) -> np.ndarray:
+        """Contrast.py:30-34; returns the ids written (for bit-exact checks)."""
+        all_size = k_all.shape[0]
+        ids = enqueue_ids(self.index, all_size, self.queue_size)
+        # index_copy_ with duplicate ids (all_size > K) is order-dependent in
+        # torch; the reference assumes all_size <= K.  numpy's
+        # fancy assignment applies in order, matching the sequential semantics.
+        for i, dst in enumerate(ids):
+            self.memory[dst] = k_all[i]
+        self.index = (self.index + all_size) % self.queue_size
+        return ids
+
+    def forward(self, q, k, k_all) -> np.ndarray:
+        out = self.logits(q, k)
+        self.enqueue(np.asarray(k_all, dtype=np.float32))
+        return out
+
+
+def logsumexp_rows(x: np.ndarray) -> np.ndarray:
+    m = x.max(axis=1, keepdims=True)
+    return (m + np.log(np.exp(x - m).sum(axis=1, keepdims=True)))[:, 0]
+
+
+def nce_softmax_loss(out: np.ndarray) -> float:
+    """moco/NCE/NCECriterion.py:11-13 -- CrossEntropyLoss(out, label 0), mean."""
+    x = out.astype(np.float64)
+    return float((logsumexp_rows(x) - x[:, 0]).mean())
+
+
+def nce_rows(out: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Per-row (lse, loss, prob) -- loss_i = lse_i - x_i0; prob_i = exp(x_i0 - lse_i)."""
+    x = out.astype(np.float64)
+    lse = logsumexp_rows(x)
+    return lse, lse - x[:, 0], np.exp(x[:, 0] - lse)
+
+
+def prob_metric(out: np.ndarray) -> float:
+    """train.py:264 -- softmax(out, 1)[:, 0].mean()."""
+    return float(nce_rows(out)[2].mean())
+
+
+def nce_backward_dq(q: np.ndarray, k: np.ndarray, memory_pre: np.ndarray,
+                    temperature: float, grad_loss: float = 1.0) -> np.ndarray:
+    """Autograd of train.py:262-263,273 w.r.t. q only (k, memory detached,
+    Contrast.py:21,25):  dx_ij = (softmax_ij - [j==0]) / N,
+    dq_i = (1/T) * (dx_i0 * k_i + sum_j dx_i,j+1 * memory_pre[j])."""
+    q64, k64, m64 = (a.astype(np.float64) for a in (q, k, memory_pre))
+    n = q.shape[0]
+    x = np.concatenate([(q64 * k64).sum(-1, keepdims=True), q64 @ m64.T], axis=1) / temperature
+    lse = logsumexp_rows(x)
+    p = np.exp(x - lse[:, None])
+    p[:, 0] -= 1.0
+    dx = p * (grad_loss / n)
+    dq = (dx[:, :1] * k64 + dx[:, 1:] @ m64) / temperature
+    return dq
+
+
+def nce_backward_dense(grad_out: np.ndarray, k: np.ndarray, memory_pre: np.ndarray,
+                       temperature: float) -> np.ndarray:
+    """Backward of Contrast.py:23-27 for an arbitrary upstream dense grad."""
+    g = grad_out.astype(np.float64) / temperature
+    return g[:, :1] * k.astype(np.float64) + g[:, 1:] @ memory_pre.astype(np.float64)
+
+
+# --------------------------------------------------------------------------
+# helpers shared by tests
+# --------------------------------------------------------------------------
+
+
+def bf16_round(x: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even fp32 -> bf16 -> fp32 (so GPU and oracle see the
+    same bf16-representable inputs; SURVEY §7 'bf16 parity definition')."""
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    rounded = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return (rounded & 0xFFFFFFFF).astype(np.uint32).view(np.float32).reshape(a.shape)
+
+
+def l2_normalize(x: np.ndarray) -> np.ndarray:
+    """moco/models/resnet.py:30-33 -- x / sqrt(sum x^2)."""
+    return x / np.sqrt((x * x).sum(axis=1, keepdims=True))

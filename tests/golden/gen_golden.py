@@ -1,0 +1,138 @@
+"""Generate golden fixtures by RUNNING THE UNMODIFIED REFERENCE (bl0/moco).
+
+Run in the build container only (``/root/reference`` does not exist on the
+GPU box):
+
+    python tests/golden/gen_golden.py
+
+It imports ``moco.NCE`` / ``moco.util`` read-only from ``/root/reference`` with
+the CPU shims SURVEY.md §8c lists (identity ``.cuda()``, gloo instead of nccl;
+no reference file is modified or copied), feeds seeded inputs through
+``MemoryMoCo`` / ``NCESoftmaxLoss`` / ``DistributedShufle`` and writes the
+inputs AND the reference's outputs to ``tests/golden/*.npz``.  The committed
+fixtures are what pins ``oracle/moco_oracle.py`` (and through it the CUDA path).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn.functional as F
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _shim():
+    sys.path.insert(0, REF)
+    torch.Tensor.cuda = lambda self, *a, **k: self          # Contrast.py:32, util.py:104-108
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+
+
+def bf16r(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+# ------------------------------------------------------------------ shuffle ids
+def gen_shuffle_ids():
+    from moco.util import DistributedShufle
+    out = {}
+    for bsz, epoch in [(8, 7), (32, 1), (64, 2), (256, 1), (2048, 1), (2048, 200), (4096, 13), (6, 0)]:
+        fwd, bwd = DistributedShufle.get_shuffle_ids(bsz, epoch)
+        out[f"fwd_{bsz}_{epoch}"] = fwd.numpy()
+        out[f"bwd_{bsz}_{epoch}"] = bwd.numpy()
+    np.savez_compressed(os.path.join(OUT, "shuffle_ids.npz"), **out)
+
+
+# ------------------------------------------------------------------ contrast head
+def gen_contrast():
+    from moco.NCE import MemoryMoCo, NCESoftmaxLoss
+    cases = {
+        # name: (N, C, K, all_size, T, start_index, steps)
+        "c1head": (32, 128, 1024, 32, 0.07, 0, 3),
+        "wrap": (8, 64, 40, 16, 0.07, 0, 4),          # K not a multiple of all_size: wraps mid-batch at step 3
+        "c256": (16, 256, 512, 32, 0.2, 0, 2),
+        "ragged": (5, 128, 77, 10, 0.1, 0, 3),
+    }
+    out = {}
+    for name, (N, C, K, A, T, idx0, steps) in cases.items():
+        torch.manual_seed(1000 + sorted(cases).index(name))
+        contrast = MemoryMoCo(C, K, T)
+        contrast.index = idx0
+        crit = NCESoftmaxLoss()
+        out[f"{name}_meta"] = np.array([N, C, K, A, steps], dtype=np.int64)
+        out[f"{name}_T"] = np.array([T], dtype=np.float64)
+        # make the initial queue bf16-representable so GPU(bf16) and oracle(fp32) agree exactly
+        contrast.memory.copy_(bf16r(contrast.memory))
+        out[f"{name}_memory0"] = contrast.memory.numpy().copy()
+        for s in range(steps):
+            q = bf16r(F.normalize(torch.randn(N, C), dim=1)).requires_grad_(True)
+            k = bf16r(F.normalize(torch.randn(N, C), dim=1))
+            k_all = bf16r(F.normalize(torch.randn(A, C), dim=1))
+            k_all[:min(N, A)] = k[:min(N, A)]                   # this rank's keys lead k_all (rank 0 view)
+            index_before = contrast.index
+            logits = contrast(q, k, k_all)                      # reference forward (+enqueue)
+            loss = crit(logits)
+            prob = F.softmax(logits, dim=1)[:, 0].mean()       # train.py:264
+            loss.backward()                                     # train.py:273
+            out[f"{name}_s{s}_q"] = q.detach().numpy().copy()
+            out[f"{name}_s{s}_k"] = k.numpy().copy()
+            out[f"{name}_s{s}_k_all"] = k_all.numpy().copy()
+            out[f"{name}_s{s}_logits"] = logits.detach().numpy().copy()
+            out[f"{name}_s{s}_loss"] = np.array([loss.item()], dtype=np.float64)
+            out[f"{name}_s{s}_prob"] = np.array([prob.item()], dtype=np.float64)
+            out[f"{name}_s{s}_dq"] = q.grad.numpy().copy()
+            out[f"{name}_s{s}_index"] = np.array([index_before, contrast.index], dtype=np.int64)
+            if s == steps - 1:                                  # keep fixtures small: final queue only
+                out[f"{name}_memory_final"] = contrast.memory.numpy().copy()
+    # state_dict keys (Contrast.py:15,18)
+    sd = MemoryMoCo(128, 16, 0.07).state_dict()
+    out["state_dict_keys"] = np.array(sorted(sd.keys()))
+    out["state_dict_params"] = sd["params"].numpy()
+    np.savez_compressed(os.path.join(OUT, "contrast.npz"), **out)
+
+
+# ------------------------------------------------------------------ ShuffleBN over gloo
+def _shuffle_worker(rank, world, n, epoch, port, ret):
+    _shim()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from moco.util import DistributedShufle
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randn(n, 3, 4, 4, generator=g)                    # "images" (small spatial dims)
+    x_shuf, binds = DistributedShufle.forward_shuffle(x, epoch)
+    # a stand-in "key encoder": per-row features that depend only on the row content
+    feat = x_shuf.reshape(n, -1)[:, :16].contiguous()
+    feat_all, feat_local = DistributedShufle.backward_shuffle(feat, binds, return_local=True)
+    ret[rank] = dict(x=x.numpy(), x_shuf=x_shuf.numpy(), binds=binds.numpy(),
+                     feat=feat.numpy(), feat_all=feat_all.numpy(), feat_local=feat_local.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def gen_shuffle():
+    out = {}
+    port = 29611
+    for world, n, epoch in [(1, 8, 3), (2, 4, 7), (4, 6, 2)]:
+        mgr = mp.Manager()
+        ret = mgr.dict()
+        mp.spawn(_shuffle_worker, args=(world, n, epoch, port, ret), nprocs=world, join=True)
+        port += 1
+        tag = f"w{world}_n{n}_e{epoch}"
+        for r in range(world):
+            for key, val in ret[r].items():
+                out[f"{tag}_r{r}_{key}"] = val
+    np.savez_compressed(os.path.join(OUT, "shuffle.npz"), **out)
+
+
+if __name__ == "__main__":
+    _shim()
+    gen_shuffle_ids()
+    gen_contrast()
+    gen_shuffle()
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)))
