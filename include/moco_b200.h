@@ -1,0 +1,160 @@
+/*
+ * moco_b200 -- C ABI of the B200-native MoCo contrastive hot path.
+ *
+ * This is the drop-in boundary.  The reference (bl0/moco) is pure
+ * Python on PyTorch and has no FFI of its own; each entry point below replaces
+ * the PyTorch library calls of one reference function (cited per function,
+ * paths relative to the reference checkout).  A binding needs nothing but raw
+ * device pointers, sizes and a cudaStream_t -- see INTEGRATION.md for the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - compute calls are asynchronous on `stream` (a cudaStream_t passed as
+ *     void*), re-entrant, allocate nothing and keep no global state besides the
+ *     cached cuTensorMapEncodeTiled entry point; they are CUDA-graph capturable;
+ *   - return value: 0 on success, a negative MOCO_ERR_* otherwise;
+ *     moco_last_error() returns a thread-local human readable message;
+ *   - row-major everywhere; `queue` is the [K, C] MoCo memory bank.
+ */
+#ifndef MOCO_B200_H
+#define MOCO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOCO_B200_ABI_VERSION 1
+
+enum {
+    MOCO_OK = 0,
+    MOCO_ERR_INVALID = -1,     /* bad argument (null pointer, size, alignment)          */
+    MOCO_ERR_UNSUPPORTED = -2, /* valid but not implemented for this shape/dtype/device */
+    MOCO_ERR_WORKSPACE = -3,   /* workspace too small                                    */
+    MOCO_ERR_CUDA = -4         /* a CUDA runtime/driver call failed                      */
+};
+
+enum { MOCO_F32 = 0, MOCO_BF16 = 1 };
+
+/* moco_nce_fwd `flags` */
+enum {
+    MOCO_NCE_AUTO = 0,         /* tcgen05 kernel when the shape allows it (C % 64 == 0, C <= 256) */
+    MOCO_NCE_FORCE_SIMT = 1,   /* generic CUDA-core kernel (any shape)                             */
+    MOCO_NCE_CTA_PAIR = 2,     /* tcgen05.mma.cta_group::2 (M = 256 per CTA pair)                  */
+    MOCO_NCE_SINGLE_CTA = 4    /* tcgen05.mma.cta_group::1 (M = 128 per CTA)                       */
+};
+
+int moco_abi_version(void);
+const char* moco_last_error(void);
+
+/* Number of SMs / compute capability of the current device (for tests & bench). */
+int moco_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------
+ * InfoNCE head:  MemoryMoCo.forward logits (moco/NCE/Contrast.py:20-27) fused
+ * with NCESoftmaxLoss (moco/NCE/NCECriterion.py:11-13), the `prob` metric
+ * (train.py:264) and -- optionally, in the same pass over the queue -- the
+ * gradient autograd would produce at train.py:273.
+ *
+ *   x[i,0]   = <q_i, k_i> * inv_T                       (positive, column 0)
+ *   x[i,1+j] = <bf16(q_i), queue_j> * inv_T             (K negatives)
+ *   lse[i]   = log sum_j exp(x[i,j]);  loss_rows[i] = lse[i] - x[i,0];
+ *   prob_rows[i] = exp(x[i,0] - lse[i]);  loss_prob = {mean loss, mean prob}
+ *   dq[i]    = d(mean loss)/dq_i
+ *            = inv_T / N * ( (p_i0 - 1) * k_i + sum_j p_i,1+j * queue_j ),  p = softmax(x)
+ *              (gradient w.r.t. q only: k and the queue are detached, Contrast.py:21,25)
+ *
+ * q, k: [N, C] of `qk_dtype` (MOCO_F32 or MOCO_BF16).  queue: [K, C] bf16, the
+ * PRE-enqueue snapshot (Contrast.py:25) -- call moco_queue_enqueue afterwards on
+ * the same stream.  Because dq is produced here, before the enqueue, no clone of
+ * the queue is ever needed (the reference clones it every step, Contrast.py:24-25).
+ * The contractions run on tcgen05 tensor cores with bf16 operands (q is rounded
+ * to bf16 when given as f32) and fp32 accumulation; the positive logit is
+ * computed in fp32 from the inputs as given.
+ * `logits` ([N, K+1] fp32, row stride K+1) may be NULL: then no logit ever
+ * reaches HBM.  `dq` ([N, C] fp32) may be NULL.  lse / loss_rows / prob_rows:
+ * [N] fp32; loss_prob: [2] fp32.  All reductions are deterministic (fixed
+ * order, no float atomics).
+ * ---------------------------------------------------------------------- */
+size_t moco_nce_workspace_bytes(int N, int C, int K);
+
+int moco_nce_fwd(const void* q, const void* k, int qk_dtype,
+                 const void* queue_bf16, int N, int C, int K, float inv_T,
+                 float* logits_or_null, float* lse, float* loss_rows, float* prob_rows,
+                 float* loss_prob, float* dq_or_null,
+                 void* workspace, size_t workspace_bytes, int flags, void* stream);
+
+/* Backward of the dense-logits compatibility API (MemoryMoCo.forward returning
+ * `out`, then an arbitrary upstream gradient):
+ *   dq_i = inv_T * ( g_i0 * k_i + sum_j g_i,1+j * queue_j ),  g = grad_logits [N, K+1] fp32.
+ * `queue_bf16` must be the PRE-enqueue snapshot the forward saw. */
+int moco_nce_bwd_dense(const float* grad_logits, const void* k, int k_dtype,
+                       const void* queue_bf16, int N, int C, int K, float inv_T,
+                       float* dq, void* stream);
+
+/* ------------------------------------------------------------------------
+ * FIFO enqueue (moco/NCE/Contrast.py:29-34):
+ *   for i in [0, n_all): queue[(index + i) mod K] = k_all[i]
+ * `index` is the write pointer BEFORE the call; the caller advances it
+ * ((index + n_all) mod K, Contrast.py:34).  Writes the bf16 working queue and,
+ * when non-NULL, the fp32 master copy (the checkpointed `memory` buffer,
+ * Contrast.py:18).  Requires n_all <= K.
+ * ---------------------------------------------------------------------- */
+int moco_queue_enqueue(void* queue_bf16, float* queue_f32_or_null,
+                       const void* k_all, int k_dtype, int n_all, int C, int64_t K,
+                       int64_t index, void* stream);
+
+/* fp32 -> bf16 (round-to-nearest-even); used to (re)build the bf16 working queue
+ * from the fp32 `memory` buffer (init / load_state_dict). */
+int moco_f32_to_bf16(const float* src, void* dst_bf16, size_t n_elems, void* stream);
+
+/* ------------------------------------------------------------------------
+ * ShuffleBN row gather over NVLink peer memory.  Replaces dist_collect +
+ * fancy-index (moco/util.py:47-58,74-79,88-91): instead of all_gather-ing every
+ * rank's batch and indexing, each rank pulls exactly the rows it needs.
+ *
+ *   for i in [0, n_rows): g = src_rows[i];
+ *       dst[i] = peer_base_host[g / rows_per_rank] + (g % rows_per_rank) * row_bytes
+ *
+ * peer_base_host: HOST array of `world` device pointers (peer-mapped buffers from
+ * moco_p2p_* below; world = 1 -> the local buffer).  src_rows: DEVICE int64
+ * [n_rows] global row ids (the slice of forward_inds / backward_inds this rank
+ * needs, util.py:77,91).  row_bytes must be a multiple of 16 and buffers 16-byte
+ * aligned.  Synchronisation with the peers (data ready / buffer reusable) is the
+ * caller's: moco_signal_barrier.
+ * flags: MOCO_GATHER_AUTO = bulk-async (TMA) copies for rows >= 16 KiB, one warp
+ * per row below; MOCO_GATHER_LDG = plain 16-byte load/store kernel for large rows.
+ * ---------------------------------------------------------------------- */
+enum { MOCO_GATHER_AUTO = 0, MOCO_GATHER_LDG = 1 };
+int moco_shuffle_gather(const void* const* peer_base_host, int world, int rows_per_rank,
+                        const int64_t* src_rows, int n_rows, size_t row_bytes,
+                        void* dst, int flags, void* stream);
+
+/* Cross-GPU stream-ordered barrier on peer-mapped signal pads (one uint32 slot
+ * per writer rank on every rank): every rank stores `epoch` into slot[rank] of
+ * every peer's pad (release, system scope), then waits until all `world` slots
+ * of its own pad are >= epoch (acquire).  signal_pads_host: HOST array of `world`
+ * device pointers to the pads (each >= world * 4 bytes, zero-initialised).
+ * `epoch` must increase by 1 per call.  The spin is bounded (traps, never hangs). */
+int moco_signal_barrier(void* const* signal_pads_host, int world, int rank,
+                        uint32_t epoch, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Peer-memory plumbing for the two calls above (synchronous host functions;
+ * the only entry points that allocate).  A buffer is cudaMalloc'ed and zeroed,
+ * its 64-byte CUDA IPC handle is exchanged by the caller over its existing
+ * process group (the reference's torch.distributed group, train.py:300), and
+ * each peer maps it with moco_p2p_open (cudaIpcOpenMemHandle, lazy peer access).
+ * ---------------------------------------------------------------------- */
+int moco_p2p_alloc(size_t bytes, void** dev_ptr_out, unsigned char handle_out[64]);
+int moco_p2p_open(const unsigned char handle[64], void** dev_ptr_out);
+int moco_p2p_close(void* dev_ptr);
+int moco_p2p_free(void* dev_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOCO_B200_H */

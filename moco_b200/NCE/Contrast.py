@@ -1,0 +1,206 @@
+"""MemoryMoCo -- the MoCo queue + InfoNCE head behind the reference's own API.
+
+Mirrors ``moco/NCE/Contrast.py:6-36`` of bl0/moco (same constructor, attributes,
+buffers, ``state_dict`` keys and ``forward(q, k, k_all) -> [N, K+1]`` contract) but
+every device-side step is a hand-written sm_100a kernel reached through the C ABI
+(``include/moco_b200.h``):
+
+* ``forward_loss(q, k, k_all) -> (loss, prob)``: the fused fast path.  The
+  q.Queue^T contraction, /T, log-sum-exp, cross-entropy, ``prob`` metric AND the
+  gradient w.r.t. q are produced by tcgen05 kernels before the enqueue; the
+  [N, K+1] logits never reach HBM and the queue is never cloned.
+* ``forward(q, k, k_all) -> out``: API-compatible dense logits (the kernel's
+  epilogue writes them).  The returned tensor also carries the fused loss so that
+  ``NCESoftmaxLoss`` (NCECriterion.py) does not have to re-read it.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from .. import _lib
+
+
+class _Scratch:
+    """Per-(N, C, K, device) output + workspace buffers (allocated once; stable
+    addresses keep the calls CUDA-graph capturable)."""
+
+    def __init__(self, N, C, K, device):
+        lib = _lib.load()
+        f32 = dict(dtype=torch.float32, device=device)
+        self.lse = torch.empty(N, **f32)
+        self.loss_rows = torch.empty(N, **f32)
+        self.prob_rows = torch.empty(N, **f32)
+        self.ws_bytes = int(lib.moco_nce_workspace_bytes(N, C, K))
+        self.ws = torch.empty(self.ws_bytes + 256, dtype=torch.uint8, device=device)
+        off = (-self.ws.data_ptr()) % 256
+        self.ws_ptr = self.ws.data_ptr() + off
+
+
+def _nce_forward(mod: "MemoryMoCo", q, k, want_logits: bool, want_dq: bool, flags: int):
+    lib = _lib.load()
+    _lib.require_cuda(q, k, mod.memory)
+    if q.dim() != 2 or q.shape != k.shape or q.shape[1] != mod.memory.shape[1]:
+        raise ValueError(f"MemoryMoCo: q {tuple(q.shape)} / k {tuple(k.shape)} do not match the queue "
+                         f"{tuple(mod.memory.shape)}")
+    if q.dtype != k.dtype:
+        k = k.to(q.dtype)
+    q = q.contiguous()
+    k = k.contiguous()
+    N, C = q.shape
+    K = mod.queue_size
+    queue = mod._queue_bf16()
+    key = (N, C, K, q.device)
+    sc = mod._scratch.get(key)
+    if sc is None:
+        sc = mod._scratch[key] = _Scratch(N, C, K, q.device)
+    logits = torch.empty(N, K + 1, dtype=torch.float32, device=q.device) if want_logits else None
+    dq = torch.empty(N, C, dtype=torch.float32, device=q.device) if want_dq else None
+    loss_prob = torch.empty(2, dtype=torch.float32, device=q.device)
+    code = lib.moco_nce_fwd(
+        q.data_ptr(), k.data_ptr(), _lib.dtype_code(q), queue.data_ptr(), N, C, K,
+        1.0 / mod.temperature,
+        logits.data_ptr() if logits is not None else None,
+        sc.lse.data_ptr(), sc.loss_rows.data_ptr(), sc.prob_rows.data_ptr(), loss_prob.data_ptr(),
+        dq.data_ptr() if dq is not None else None,
+        sc.ws_ptr, sc.ws_bytes, flags, _lib.cur_stream())
+    _lib.check(code, "moco_nce_fwd")
+    return logits, loss_prob, dq, q, k
+
+
+class _FusedNCE(torch.autograd.Function):
+    """(loss, prob) = InfoNCE(q, k, queue); backward: grad_q = grad_loss * dq (dq from the forward)."""
+
+    @staticmethod
+    def forward(ctx, q, k, mod, flags):
+        need_dq = q.requires_grad
+        _, loss_prob, dq, _, _ = _nce_forward(mod, q.detach(), k.detach(), False, need_dq, flags)
+        ctx.dq = dq
+        ctx.q_dtype = q.dtype
+        loss, prob = loss_prob[0], loss_prob[1]
+        ctx.mark_non_differentiable(prob)
+        return loss, prob
+
+    @staticmethod
+    def backward(ctx, g_loss, g_prob):
+        dq = ctx.dq
+        if dq is None:
+            return None, None, None, None
+        return (dq * g_loss).to(ctx.q_dtype), None, None, None
+
+
+class _FusedNCEWithLogits(torch.autograd.Function):
+    """Dense-logits API: returns (out, loss, prob).  ``out`` has the dense backward
+    (arbitrary upstream gradient); ``loss`` has the fused backward."""
+
+    @staticmethod
+    def forward(ctx, q, k, mod, flags):
+        need = q.requires_grad
+        logits, loss_prob, dq, qc, kc = _nce_forward(mod, q.detach(), k.detach(), True, need, flags)
+        ctx.dq = dq
+        ctx.q_dtype = q.dtype
+        ctx.inv_T = 1.0 / mod.temperature
+        ctx.K = mod.queue_size
+        if need:
+            # the dense backward needs the PRE-enqueue queue (the reference clones it too, Contrast.py:25)
+            ctx.save_for_backward(kc, mod._queue_bf16().clone())
+        loss, prob = loss_prob[0], loss_prob[1]
+        ctx.mark_non_differentiable(prob)
+        return logits, loss, prob
+
+    @staticmethod
+    def backward(ctx, g_out, g_loss, g_prob):
+        if ctx.dq is None:
+            return None, None, None, None
+        grad = None
+        if g_loss is not None:
+            grad = ctx.dq * g_loss
+        if g_out is not None:
+            kc, queue_pre = ctx.saved_tensors
+            lib = _lib.load()
+            g = g_out.contiguous().float()
+            N, C = kc.shape
+            dq2 = torch.empty(N, C, dtype=torch.float32, device=g.device)
+            code = lib.moco_nce_bwd_dense(g.data_ptr(), kc.data_ptr(), _lib.dtype_code(kc), queue_pre.data_ptr(),
+                                          N, C, ctx.K, ctx.inv_T, dq2.data_ptr(), _lib.cur_stream())
+            _lib.check(code, "moco_nce_bwd_dense")
+            grad = dq2 if grad is None else grad + dq2
+        return (grad.to(ctx.q_dtype) if grad is not None else None), None, None, None
+
+
+class MemoryMoCo(nn.Module):
+    """Fixed-size queue with momentum encoder (drop-in for moco.NCE.MemoryMoCo)."""
+
+    def __init__(self, feature_dim, queue_size, temperature=0.07):
+        super().__init__()
+        self.queue_size = queue_size
+        self.temperature = temperature
+        self.index = 0
+        self.kernel_flags = _lib.NCE_AUTO
+
+        # same buffers / init / state_dict keys as the reference (Contrast.py:15-18)
+        self.register_buffer('params', torch.tensor([-1]))
+        stdv = 1. / math.sqrt(feature_dim / 3)
+        memory = torch.rand(self.queue_size, feature_dim, requires_grad=False).mul_(2 * stdv).add_(-stdv)
+        self.register_buffer('memory', memory)
+        # bf16 working copy read by the tensor-core kernels; rebuilt from `memory` on demand
+        self.register_buffer('memory_bf16', torch.empty(0, dtype=torch.bfloat16), persistent=False)
+        self._bf16_src = None      # (data_ptr, _version) of `memory` the bf16 copy was built from
+        self._scratch = {}
+        self._register_load_state_dict_post_hook(lambda m, keys: m._invalidate())
+
+    # -- bf16 working queue -------------------------------------------------
+    def _invalidate(self):
+        self._bf16_src = None
+
+    def _apply(self, fn, *a, **kw):      # .cuda() / .to(): buffers move, caches die
+        out = super()._apply(fn, *a, **kw)
+        self._invalidate()
+        self._scratch = {}
+        return out
+
+    def _queue_bf16(self) -> torch.Tensor:
+        mem = self.memory
+        _lib.require_cuda(mem)
+        tag = (mem.data_ptr(), mem._version)
+        if self._bf16_src != tag or self.memory_bf16.shape != mem.shape or self.memory_bf16.device != mem.device:
+            if self.memory_bf16.shape != mem.shape or self.memory_bf16.device != mem.device:
+                self.memory_bf16 = torch.empty_like(mem, dtype=torch.bfloat16)
+            lib = _lib.load()
+            _lib.check(lib.moco_f32_to_bf16(mem.data_ptr(), self.memory_bf16.data_ptr(), mem.numel(),
+                                            _lib.cur_stream()), "moco_f32_to_bf16")
+            self._bf16_src = tag
+        return self.memory_bf16
+
+    # -- enqueue (Contrast.py:29-34) ----------------------------------------
+    @torch.no_grad()
+    def enqueue(self, k_all):
+        lib = _lib.load()
+        _lib.require_cuda(k_all)
+        k_all = k_all.detach().contiguous()
+        all_size, C = k_all.shape
+        queue = self._queue_bf16()
+        code = lib.moco_queue_enqueue(queue.data_ptr(), self.memory.data_ptr(), k_all.data_ptr(),
+                                      _lib.dtype_code(k_all), all_size, C, self.queue_size, self.index,
+                                      _lib.cur_stream())
+        _lib.check(code, "moco_queue_enqueue")
+        # the kernel wrote both copies; keep the cache tag in sync without bumping `memory._version`
+        self._bf16_src = (self.memory.data_ptr(), self.memory._version)
+        self.index = (self.index + all_size) % self.queue_size
+
+    # -- public API ----------------------------------------------------------
+    def forward_loss(self, q, k, k_all):
+        """Fused path: returns (loss, prob) == (NCESoftmaxLoss()(out), softmax(out,1)[:,0].mean())
+        of the reference's train.py:262-264, then enqueues k_all."""
+        loss, prob = _FusedNCE.apply(q, k.detach(), self, self.kernel_flags)
+        self.enqueue(k_all)
+        return loss, prob
+
+    def forward(self, q, k, k_all):
+        out, loss, prob = _FusedNCEWithLogits.apply(q, k.detach(), self, self.kernel_flags)
+        self.enqueue(k_all)
+        # let NCESoftmaxLoss pick up the fused result instead of re-reading [N, K+1] logits
+        out._moco_fused = (loss, prob, out._version)
+        return out

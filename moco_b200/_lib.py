@@ -1,0 +1,96 @@
+"""ctypes binding of libmoco_b200.so (the C ABI in include/moco_b200.h).
+
+The library is built in-tree by ``moco_b200/build.py`` (nvcc, sm_100a).  There is
+no CPU fallback: if the shared object is missing and cannot be built, importing
+any compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_uint32, c_void_p
+
+from . import build as _build
+
+MOCO_F32, MOCO_BF16 = 0, 1
+NCE_AUTO, NCE_FORCE_SIMT, NCE_CTA_PAIR, NCE_SINGLE_CTA = 0, 1, 2, 4
+GATHER_AUTO, GATHER_LDG = 0, 1
+
+# every symbol include/moco_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "moco_abi_version": (c_int, []),
+    "moco_last_error": (c_char_p, []),
+    "moco_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "moco_nce_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "moco_nce_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
+                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_size_t, c_int, c_void_p]),
+    "moco_nce_bwd_dense": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
+                                   c_void_p, c_void_p]),
+    "moco_queue_enqueue": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_void_p]),
+    "moco_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "moco_shuffle_gather": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p]),
+    "moco_signal_barrier": (c_int, [POINTER(c_void_p), c_int, c_int, c_uint32, c_void_p]),
+    "moco_p2p_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "moco_p2p_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "moco_p2p_close": (c_int, [c_void_p]),
+    "moco_p2p_free": (c_int, [c_void_p]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load() -> ctypes.CDLL:
+    """Load (building first if needed and possible) libmoco_b200.so."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    import torch  # noqa: F401  (loads the CUDA runtime the library links against)
+    path = _build.LIB
+    if not os.path.exists(path):
+        try:
+            _build.build()
+        except Exception as exc:  # no nvcc on this box and no prebuilt library
+            raise RuntimeError(
+                f"moco_b200: {path} is missing and could not be built ({exc}); "
+                "there is no CPU fallback for the CUDA hot path") from exc
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.moco_abi_version() != 1:
+        raise RuntimeError("moco_b200: ABI version mismatch between _lib.py and libmoco_b200.so")
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().moco_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"moco_b200.{what} failed ({code}): {msg}")
+
+
+def dtype_code(t) -> int:
+    import torch
+    if t.dtype == torch.float32:
+        return MOCO_F32
+    if t.dtype == torch.bfloat16:
+        return MOCO_BF16
+    raise TypeError(f"moco_b200: unsupported dtype {t.dtype} (expected float32 or bfloat16)")
+
+
+def cur_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("moco_b200: the contrastive hot path runs on CUDA only "
+                               "(got a CPU tensor); there is no CPU fallback")

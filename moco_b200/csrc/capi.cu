@@ -1,0 +1,249 @@
+// extern "C" boundary of libmoco_b200.so (see include/moco_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/moco_b200.h"
+#include "common.cuh"
+
+namespace moco {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int cuda_fail(const char* what, cudaError_t e) {
+    if (e == cudaErrorNotSupported) {
+        set_error("%s: shape/device not supported by this kernel", what);
+        return MOCO_ERR_UNSUPPORTED;
+    }
+    if (g_err[0] == 0 || e != cudaErrorUnknown) set_error("%s: %s", what, cudaGetErrorString(e));
+    return MOCO_ERR_CUDA;
+}
+
+struct DevInfo { int sms; int major; int minor; bool ok; };
+static DevInfo device_info() {
+    static DevInfo cache[64];
+    static bool have[64] = {false};
+    int dev = 0;
+    DevInfo d = {0, 0, 0, false};
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return d;
+    if (have[dev]) return cache[dev];
+    if (cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return d;
+    cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&d.minor, cudaDevAttrComputeCapabilityMinor, dev);
+    d.ok = true;
+    cache[dev] = d;
+    have[dev] = true;
+    return d;
+}
+
+}  // namespace moco
+
+using namespace moco;
+
+extern "C" {
+
+int moco_abi_version(void) { return MOCO_B200_ABI_VERSION; }
+
+const char* moco_last_error(void) { return g_err; }
+
+int moco_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    DevInfo d = device_info();
+    if (!d.ok) { set_error("no CUDA device"); return MOCO_ERR_CUDA; }
+    if (sm_count) *sm_count = d.sms;
+    if (cc_major) *cc_major = d.major;
+    if (cc_minor) *cc_minor = d.minor;
+    return MOCO_OK;
+}
+
+size_t moco_nce_workspace_bytes(int N, int C, int K) {
+    (void)K;
+    if (N <= 0 || C <= 0) return 0;
+    return carve_workspace(nullptr, N, C).bytes;
+}
+
+int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_bf16, int N, int C, int K,
+                 float inv_T, float* logits, float* lse, float* loss_rows, float* prob_rows, float* loss_prob,
+                 float* dq, void* workspace, size_t workspace_bytes, int flags, void* stream_) {
+    g_err[0] = 0;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!q || !k || !queue_bf16 || !lse || !loss_rows || !prob_rows || !loss_prob || !workspace) {
+        set_error("moco_nce_fwd: null pointer argument");
+        return MOCO_ERR_INVALID;
+    }
+    if (N <= 0 || C <= 0 || K <= 0 || !(inv_T > 0.f) || (qk_dtype != MOCO_F32 && qk_dtype != MOCO_BF16)) {
+        set_error("moco_nce_fwd: bad N/C/K/inv_T/dtype (N=%d C=%d K=%d inv_T=%g dtype=%d)", N, C, K, (double)inv_T, qk_dtype);
+        return MOCO_ERR_INVALID;
+    }
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+        set_error("moco_nce_fwd: workspace must be 256-byte aligned");
+        return MOCO_ERR_INVALID;
+    }
+    NceWorkspace ws = carve_workspace(workspace, N, C);
+    if (workspace_bytes < ws.bytes) {
+        set_error("moco_nce_fwd: workspace too small (%zu < %zu)", workspace_bytes, ws.bytes);
+        return MOCO_ERR_WORKSPACE;
+    }
+    DevInfo d = device_info();
+    if (!d.ok) { set_error("moco_nce_fwd: no CUDA device"); return MOCO_ERR_CUDA; }
+
+    cudaError_t e = launch_prep(q, k, qk_dtype, N, C, ws, stream);
+    if (e != cudaSuccess) return cuda_fail("prep kernel", e);
+    const __nv_bfloat16* qb = qk_dtype == MOCO_BF16 ? static_cast<const __nv_bfloat16*>(q) : ws.q_bf16;
+    const __nv_bfloat16* queue = static_cast<const __nv_bfloat16*>(queue_bf16);
+
+    const bool tc_shape = (C % 64 == 0) && C <= 256 && ((reinterpret_cast<uintptr_t>(qb) & 15) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(queue) & 15) == 0);
+    const bool want_tc = !(flags & MOCO_NCE_FORCE_SIMT);
+    if ((flags & (MOCO_NCE_CTA_PAIR | MOCO_NCE_SINGLE_CTA)) && (!tc_shape || d.major != 10)) {
+        set_error("moco_nce_fwd: tcgen05 path requested but unavailable (C=%d, sm_%d%d)", C, d.major, d.minor);
+        return MOCO_ERR_UNSUPPORTED;
+    }
+    if (want_tc && tc_shape && d.major == 10) {
+        NceTcParams p;
+        p.q_bf16 = qb; p.queue = queue; p.N = N; p.C = C; p.K = K; p.inv_T = inv_T; p.logits = logits;
+        p.cta_group = (flags & MOCO_NCE_CTA_PAIR) ? 2 : 1;
+        p.num_sms = d.sms;
+        p.slices = 0; p.n_pad = 0;
+        e = launch_nce_tc(p, ws, stream);
+        if (e == cudaSuccess) {
+            e = launch_combine(N, C, p.slices, p.n_pad, inv_T, logits, K, lse, loss_rows, prob_rows, loss_prob, ws, stream);
+            if (e != cudaSuccess) return cuda_fail("combine kernel", e);
+            if (dq) {
+                int slices = 0, n_pad = 0;
+                e = launch_nce_dq_tc(qb, queue, N, C, K, inv_T, lse, d.sms, &slices, &n_pad, ws, stream);
+                if (e != cudaSuccess) return cuda_fail("tcgen05 dq kernel", e);
+                e = launch_dq_reduce(N, C, slices, n_pad, inv_T, k, qk_dtype, prob_rows, dq, ws, stream);
+                if (e != cudaSuccess) return cuda_fail("dq reduce kernel", e);
+            }
+            return MOCO_OK;
+        }
+        if (e != cudaErrorNotSupported || (flags & (MOCO_NCE_CTA_PAIR | MOCO_NCE_SINGLE_CTA)))
+            return cuda_fail("tcgen05 stats kernel", e);
+        // shape outside the tensor-core kernel's envelope (e.g. N > 128 * #SM): generic path below
+    }
+    e = launch_simt_rows(qb, k, qk_dtype, queue, N, C, K, inv_T, logits, lse, loss_rows, prob_rows, loss_prob, dq, ws, stream);
+    if (e != cudaSuccess) return cuda_fail("generic NCE kernel", e);
+    return MOCO_OK;
+}
+
+int moco_nce_bwd_dense(const float* grad_logits, const void* k, int k_dtype, const void* queue_bf16, int N, int C,
+                       int K, float inv_T, float* dq, void* stream_) {
+    g_err[0] = 0;
+    if (!grad_logits || !k || !queue_bf16 || !dq || N <= 0 || C <= 0 || K <= 0) {
+        set_error("moco_nce_bwd_dense: bad argument");
+        return MOCO_ERR_INVALID;
+    }
+    cudaError_t e = launch_bwd_dense(grad_logits, k, k_dtype, static_cast<const __nv_bfloat16*>(queue_bf16), N, C, K,
+                                     inv_T, dq, static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return cuda_fail("dense backward kernel", e);
+    return MOCO_OK;
+}
+
+int moco_queue_enqueue(void* queue_bf16, float* queue_f32, const void* k_all, int k_dtype, int n_all, int C,
+                       int64_t K, int64_t index, void* stream_) {
+    g_err[0] = 0;
+    if (!queue_bf16 || !k_all || n_all < 0 || C <= 0 || K <= 0 || index < 0 || index >= K) {
+        set_error("moco_queue_enqueue: bad argument (n_all=%d C=%d K=%lld index=%lld)", n_all, C, (long long)K, (long long)index);
+        return MOCO_ERR_INVALID;
+    }
+    if (n_all > K) {
+        set_error("moco_queue_enqueue: n_all (%d) > K (%lld): write order would be ambiguous", n_all, (long long)K);
+        return MOCO_ERR_INVALID;
+    }
+    cudaError_t e = launch_enqueue(static_cast<__nv_bfloat16*>(queue_bf16), queue_f32, k_all, k_dtype, n_all, C, K,
+                                   index, static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return cuda_fail("enqueue kernel", e);
+    return MOCO_OK;
+}
+
+int moco_f32_to_bf16(const float* src, void* dst, size_t n, void* stream_) {
+    g_err[0] = 0;
+    if ((!src || !dst) && n) { set_error("moco_f32_to_bf16: null pointer"); return MOCO_ERR_INVALID; }
+    cudaError_t e = launch_f32_to_bf16(src, static_cast<__nv_bfloat16*>(dst), n, static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return cuda_fail("f32->bf16 kernel", e);
+    return MOCO_OK;
+}
+
+int moco_shuffle_gather(const void* const* peers, int world, int rows_per_rank, const int64_t* src_rows, int n_rows,
+                        size_t row_bytes, void* dst, int flags, void* stream_) {
+    g_err[0] = 0;
+    if (!peers || !src_rows || !dst || world < 1 || world > 16 || rows_per_rank < 1 || n_rows < 0 ||
+        row_bytes == 0 || (row_bytes & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0) {
+        set_error("moco_shuffle_gather: bad argument (world=%d rows_per_rank=%d n_rows=%d row_bytes=%zu)", world,
+                  rows_per_rank, n_rows, row_bytes);
+        return MOCO_ERR_INVALID;
+    }
+    for (int i = 0; i < world; ++i)
+        if (!peers[i] || (reinterpret_cast<uintptr_t>(peers[i]) & 15) != 0) {
+            set_error("moco_shuffle_gather: peer %d pointer null or misaligned", i);
+            return MOCO_ERR_INVALID;
+        }
+    cudaError_t e = launch_gather(peers, world, rows_per_rank, src_rows, n_rows, row_bytes, dst, flags,
+                                  static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return cuda_fail("shuffle gather kernel", e);
+    return MOCO_OK;
+}
+
+int moco_signal_barrier(void* const* pads, int world, int rank, uint32_t epoch, void* stream_) {
+    g_err[0] = 0;
+    if (!pads || world < 1 || world > 16 || rank < 0 || rank >= world) {
+        set_error("moco_signal_barrier: bad argument");
+        return MOCO_ERR_INVALID;
+    }
+    cudaError_t e = launch_signal_barrier(pads, world, rank, epoch, static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return cuda_fail("signal barrier kernel", e);
+    return MOCO_OK;
+}
+
+int moco_p2p_alloc(size_t bytes, void** dev_ptr_out, unsigned char handle_out[64]) {
+    g_err[0] = 0;
+    if (!dev_ptr_out || !handle_out || bytes == 0) { set_error("moco_p2p_alloc: bad argument"); return MOCO_ERR_INVALID; }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return cuda_fail("cudaMalloc", e);
+    e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail("cudaMemset", e); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail("cudaIpcGetMemHandle", e); }
+    memcpy(handle_out, &h, 64);
+    *dev_ptr_out = p;
+    return MOCO_OK;
+}
+
+int moco_p2p_open(const unsigned char handle[64], void** dev_ptr_out) {
+    g_err[0] = 0;
+    if (!handle || !dev_ptr_out) { set_error("moco_p2p_open: bad argument"); return MOCO_ERR_INVALID; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return cuda_fail("cudaIpcOpenMemHandle", e);
+    *dev_ptr_out = p;
+    return MOCO_OK;
+}
+
+int moco_p2p_close(void* dev_ptr) {
+    g_err[0] = 0;
+    cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+    if (e != cudaSuccess) return cuda_fail("cudaIpcCloseMemHandle", e);
+    return MOCO_OK;
+}
+
+int moco_p2p_free(void* dev_ptr) {
+    g_err[0] = 0;
+    cudaError_t e = cudaFree(dev_ptr);
+    if (e != cudaSuccess) return cuda_fail("cudaFree", e);
+    return MOCO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// Shared declarations for the moco_b200 CUDA sources.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace moco {
+
+constexpr int kMaxCtas = 160;          // upper bound on persistent CTAs (B200: 148 SMs)
+constexpr int kRowsPerCta = 128;       // q rows per CTA in the tcgen05 kernels (UMMA M per CTA)
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// Workspace layout shared by every NCE entry point.
+struct NceWorkspace {
+    unsigned int* counters;   // [4]   (zeroed by the prep kernel each call)
+    float* lpos;              // [N]   <q_i, k_i> in fp32, natural units
+    __nv_bfloat16* q_bf16;    // [N, C] bf16 copy of q (when q arrives as fp32)
+    float2* part_ms;          // [slices, N_pad] per-slice (running max, sum) in the log2 domain
+    float* part_o;            // [slices, N_pad, C] per-slice unnormalised sum_j 2^(x_ij - m) queue_j
+    size_t bytes;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline NceWorkspace carve_workspace(void* base, int N, int C) {
+    NceWorkspace w;
+    char* p = static_cast<char*>(base);
+    size_t off = 0;
+    w.counters = reinterpret_cast<unsigned int*>(p + off);            off += 256;
+    w.lpos = reinterpret_cast<float*>(p + off);                       off += align_up((size_t)N * 4, 256);
+    w.q_bf16 = reinterpret_cast<__nv_bfloat16*>(p + off);             off += align_up((size_t)N * C * 2, 256);
+    w.part_ms = reinterpret_cast<float2*>(p + off);                   off += align_up((size_t)kMaxCtas * kRowsPerCta * 8, 256);
+    w.part_o = reinterpret_cast<float*>(p + off);                     off += align_up((size_t)kMaxCtas * kRowsPerCta * C * 4, 256);
+    w.bytes = off;
+    return w;
+}
+
+// ---- launchers implemented across the .cu files (all async on `stream`) ----
+cudaError_t launch_prep(const void* q, const void* k, int qk_dtype, int N, int C,
+                        const NceWorkspace& ws, cudaStream_t stream);
+cudaError_t launch_simt_rows(const __nv_bfloat16* q_bf16, const void* k, int k_dtype,
+                             const __nv_bfloat16* queue, int N, int C, int K, float inv_T,
+                             float* logits, float* lse, float* loss_rows, float* prob_rows,
+                             float* loss_prob, float* dq, const NceWorkspace& ws, cudaStream_t stream);
+cudaError_t launch_combine(int N, int C, int slices, int n_pad, float inv_T, float* logits, int K,
+                           float* lse, float* loss_rows, float* prob_rows, float* loss_prob,
+                           const NceWorkspace& ws, cudaStream_t stream);
+cudaError_t launch_dq_reduce(int N, int C, int slices, int n_pad, float inv_T, const void* k, int k_dtype,
+                             const float* prob_rows, float* dq, const NceWorkspace& ws, cudaStream_t stream);
+cudaError_t launch_bwd_dense(const float* g, const void* k, int k_dtype, const __nv_bfloat16* queue,
+                             int N, int C, int K, float inv_T, float* dq, cudaStream_t stream);
+cudaError_t launch_enqueue(__nv_bfloat16* queue_bf16, float* queue_f32, const void* k_all, int k_dtype,
+                           int n_all, int C, int64_t K, int64_t index, cudaStream_t stream);
+cudaError_t launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t stream);
+cudaError_t launch_gather(const void* const* peers, int world, int rows_per_rank, const int64_t* src_rows,
+                          int n_rows, size_t row_bytes, void* dst, int flags, cudaStream_t stream);
+cudaError_t launch_signal_barrier(void* const* pads, int world, int rank, uint32_t epoch, cudaStream_t stream);
+
+// tcgen05 kernels (nce_sm100.cu).  Return cudaErrorNotSupported when the shape is not handled.
+struct NceTcParams {
+    const __nv_bfloat16* q_bf16;   // [N, C]
+    const __nv_bfloat16* queue;    // [K, C]
+    int N, C, K;
+    float inv_T;
+    float* logits;                 // optional dense [N, K+1]
+    int cta_group;                 // 1 or 2
+    int num_sms;
+    // outputs of the launch decision
+    int slices;
+    int n_pad;
+};
+cudaError_t launch_nce_tc(NceTcParams& p, const NceWorkspace& ws, cudaStream_t stream);
+cudaError_t launch_nce_dq_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* queue, int N, int C, int K,
+                             float inv_T, const float* lse, int num_sms, int* slices_out, int* n_pad_out,
+                             const NceWorkspace& ws, cudaStream_t stream);
+
+void set_error(const char* fmt, ...);
+
+}  // namespace moco

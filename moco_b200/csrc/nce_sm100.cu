@@ -1,0 +1,550 @@
+// tcgen05 / TMEM / TMA kernels of the InfoNCE head (sm_100a only).
+//
+//  nce_stats_kernel<G>   S = q . Queue^T on tcgen05 (cta_group::G), accumulators double-buffered in
+//                        TMEM, epilogue = x/T, online log-sum-exp per row (and optional dense logits).
+//                        Replaces torch.mm + cat + div + CrossEntropyLoss + softmax
+//                        (moco/NCE/Contrast.py:25-27, NCECriterion.py:11-13, train.py:264).
+//  nce_dq_kernel         second pass with the exact lse: S tile -> P = exp(S/T - lse) (bf16, smem)
+//                        -> O += P . Queue on tcgen05 (queue tile reused from smem as an MN-major B
+//                        operand).  Replaces autograd's backward GEMM (train.py:273) and the queue
+//                        clone it needs (Contrast.py:24-25).
+//
+// Data layout: q [N, C] bf16 and queue [K, C] bf16 are row-major in HBM ("K-major" for the S GEMM).
+// TMA stages [rows x 64 elements] boxes (128 B per row, 128B swizzle) into shared memory; a tile of
+// R rows is stored as C/64 slabs of R x 128 B.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace moco {
+
+constexpr int kSlab = 128 * 128;            // bytes of a [128 rows x 64 bf16] swizzled slab
+constexpr int kSmemBudget = 232448 - 1024;  // max dynamic smem per CTA minus alignment slack
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// =====================================================================================
+// Kernel A: per-slice softmax statistics (and optional dense logits)
+// =====================================================================================
+constexpr int kStatsBN = 256;          // queue rows per tile (UMMA N)
+constexpr int kStatsThreads = 384;     // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
+
+struct StatsArgs {
+    int N, C, K;
+    int mblks, slices, n_pad, num_tiles, stages;
+    float inv_T;
+    float* logits;        // optional [N, K+1]
+    float2* part_ms;      // [slices, n_pad]
+};
+
+template <int G>
+__global__ void __launch_bounds__(kStatsThreads, 1)
+nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_queue,
+                 const StatsArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kStageBytes = (kStatsBN / G) * 128;
+    const int kchunks = a.C >> 6;
+    const int NS = a.stages;
+    uint8_t* q_s = smem;
+    uint8_t* b_s = q_s + kchunks * kSlab;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_s + (size_t)NS * kStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NS;
+    uint64_t* tfull = bars + 2 * NS;
+    uint64_t* tempty = bars + 2 * NS + 2;
+    uint64_t* qfull = bars + 2 * NS + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 5);
+    float2* red_s = reinterpret_cast<float2*>(bars + 2 * NS + 6);   // [128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = (G == 2) ? cluster_ctarank() : 0u;
+    const int cluster_id = blockIdx.x / G;
+    const int mblk = cluster_id % a.mblks;
+    const int slice = cluster_id / a.mblks;
+    const int t0 = (int)(((long long)slice * a.num_tiles) / a.slices);
+    const int t1 = (int)(((long long)(slice + 1) * a.num_tiles) / a.slices);
+    const int row0 = (mblk * G + (int)rank) * kRowsPerCta;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_queue);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8 * G); }
+        mbar_init(qfull, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<G>(tmem_slot, 512);
+        tmem_relinquish<G>();
+    }
+    tc_fence_before();
+    if (G == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            const uint32_t qfull_addr = (G == 2) ? mapa_shared(smem_u32(qfull), 0) : smem_u32(qfull);
+            if (rank == 0) mbar_arrive_expect_tx(qfull, (uint32_t)(kchunks * kSlab * G));
+            for (int kc = 0; kc < kchunks; ++kc) {
+                if (G == 2) tma_load_2d_2sm(&tm_q, qfull_addr, q_s + kc * kSlab, kc * 64, row0);
+                else        tma_load_2d(&tm_q, qfull, q_s + kc * kSlab, kc * 64, row0);
+            }
+            int it = 0;
+            for (int t = t0; t < t1; ++t) {
+                const int brow = t * kStatsBN + (int)rank * (kStatsBN / G);
+                for (int kc = 0; kc < kchunks; ++kc, ++it) {
+                    const int st = it % NS;
+                    const uint32_t ph = (uint32_t)(it / NS) & 1u;
+                    mbar_wait(&empty[st], ph ^ 1u);
+                    if (rank == 0) mbar_arrive_expect_tx(&full[st], (uint32_t)(kStageBytes * G));
+                    if (G == 2) tma_load_2d_2sm(&tm_queue, mapa_shared(smem_u32(&full[st]), 0), b_s + (size_t)st * kStageBytes, kc * 64, brow);
+                    else        tma_load_2d(&tm_queue, &full[st], b_s + (size_t)st * kStageBytes, kc * 64, brow);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // ------------------------------------------------ MMA issuer (pair leader only)
+            const uint32_t idesc = make_idesc_bf16(128 * G, kStatsBN, 0, 0);
+            mbar_wait(qfull, 0);
+            tc_fence_after();
+            int it = 0, lt = 0;
+            for (int t = t0; t < t1; ++t, ++lt) {
+                const int acc = lt & 1;
+                const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+                mbar_wait(&tempty[acc], aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kStatsBN);
+                for (int kc = 0; kc < kchunks; ++kc, ++it) {
+                    const int st = it % NS;
+                    const uint32_t ph = (uint32_t)(it / NS) & 1u;
+                    mbar_wait(&full[st], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(q_s + kc * kSlab);
+                    const uint32_t b_addr = smem_u32(b_s + (size_t)st * kStageBytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        umma_ss<G>(d_tmem, make_sw128_desc(a_addr + k * 32, 0, 1024),
+                                   make_sw128_desc(b_addr + k * 32, 0, 1024), idesc, (uint32_t)((kc | k) != 0));
+                    }
+                    umma_commit<G>(&empty[st]);
+                }
+                umma_commit<G>(&tfull[acc]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------- epilogue (8 warps)
+        const int quarter = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int row_local = quarter * 32 + lane;
+        const int grow = row0 + row_local;
+        const float scale2 = a.inv_T * kLog2e;
+        float m = -INFINITY, s = 0.f;
+        float* lrow = (a.logits != nullptr && grow < a.N) ? a.logits + (size_t)grow * (a.K + 1) + 1 : nullptr;
+        int lt = 0;
+        for (int t = t0; t < t1; ++t, ++lt) {
+            const int acc = lt & 1;
+            const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+            mbar_wait(&tfull[acc], aph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                const int col = half * 128 + ch * 32;
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kStatsBN + col), r);
+                tmem_ld_wait();
+                const int col0 = t * kStatsBN + col;
+                const int valid = a.K - col0;
+                if (valid >= 32) {
+                    float cm = __uint_as_float(r[0]);
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(r[j]));
+                    cm *= scale2;
+                    if (cm > m) { s *= ex2(m - cm); m = cm; }
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        s0 += ex2(fmaf(__uint_as_float(r[j + 0]), scale2, -m));
+                        s1 += ex2(fmaf(__uint_as_float(r[j + 1]), scale2, -m));
+                        s2 += ex2(fmaf(__uint_as_float(r[j + 2]), scale2, -m));
+                        s3 += ex2(fmaf(__uint_as_float(r[j + 3]), scale2, -m));
+                    }
+                    s += (s0 + s1) + (s2 + s3);
+                    if (lrow) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) lrow[col0 + j] = __uint_as_float(r[j]) * a.inv_T;
+                    }
+                } else if (valid > 0) {
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (j < valid) cm = fmaxf(cm, __uint_as_float(r[j]));
+                    cm *= scale2;
+                    if (cm > m) { s *= ex2(m - cm); m = cm; }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j < valid) {
+                            s += ex2(fmaf(__uint_as_float(r[j]), scale2, -m));
+                            if (lrow) lrow[col0 + j] = __uint_as_float(r[j]) * a.inv_T;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (G == 2) mbar_arrive_cluster(&tempty[acc], 0);
+                else        mbar_arrive(&tempty[acc]);
+            }
+        }
+        // combine the two column halves of each row, then publish the slice partial
+        if (half == 1) red_s[row_local] = make_float2(m, s);
+        named_bar_sync(1, 256);
+        if (half == 0) {
+            float2 o = red_s[row_local];
+            float M = fmaxf(m, o.x);
+            float S = 0.f;
+            if (m != -INFINITY) S += s * ex2(m - M);
+            if (o.x != -INFINITY) S += o.y * ex2(o.x - M);
+            a.part_ms[(size_t)slice * a.n_pad + grow] = make_float2(M, S);
+        }
+    }
+
+    tc_fence_before();
+    if (G == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) tmem_dealloc<G>(tmem_base, 512);
+}
+
+// =====================================================================================
+// Kernel B: dq pass.  O[128, C] += P[128, 128] . Queue_tile[128, C] with P = 2^(S*scale2 - lse2)
+// =====================================================================================
+constexpr int kDqBN = 128;
+constexpr int kDqThreads = 384;
+
+struct DqArgs {
+    int N, C, K;
+    int mblks, slices, n_pad, num_tiles, stages;
+    float inv_T;
+    const float* lse;     // [N] natural log
+    float* part_o;        // [slices, n_pad, C]
+};
+
+__global__ void __launch_bounds__(kDqThreads, 1)
+nce_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_queue,
+              const DqArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int kchunks = a.C >> 6;
+    const int NS = a.stages;
+    const int tile_bytes = kchunks * kSlab;          // [128 rows x C] as C/64 slabs
+    uint8_t* q_s = smem;
+    uint8_t* p_s = q_s + tile_bytes;                 // P tile: 2 slabs (128 rows x 128 cols bf16)
+    uint8_t* v_s = p_s + 2 * kSlab;                  // NS queue tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + (size_t)NS * tile_bytes);
+    uint64_t* kv_full = bars;
+    uint64_t* kv_empty = bars + NS;
+    uint64_t* s_full = bars + 2 * NS;        // [2]
+    uint64_t* s_empty = bars + 2 * NS + 2;   // [2]
+    uint64_t* p_full = bars + 2 * NS + 4;
+    uint64_t* p_empty = bars + 2 * NS + 5;
+    uint64_t* o_full = bars + 2 * NS + 6;
+    uint64_t* qfull = bars + 2 * NS + 7;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mblk = blockIdx.x % a.mblks;
+    const int slice = blockIdx.x / a.mblks;
+    const int t0 = (int)(((long long)slice * a.num_tiles) / a.slices);
+    const int t1 = (int)(((long long)(slice + 1) * a.num_tiles) / a.slices);
+    const int ntiles = t1 - t0;
+    const int row0 = mblk * kRowsPerCta;
+    // TMEM columns: S buffers at [0,128) and [128,256); O at [256, 256 + C)
+    constexpr uint32_t kOCol = 256;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_queue);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 8); }
+        mbar_init(p_full, 8);
+        mbar_init(p_empty, 1);
+        mbar_init(o_full, 1);
+        mbar_init(qfull, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<1>(tmem_slot, 512);
+        tmem_relinquish<1>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            mbar_arrive_expect_tx(qfull, (uint32_t)tile_bytes);
+            for (int kc = 0; kc < kchunks; ++kc) tma_load_2d(&tm_q, qfull, q_s + kc * kSlab, kc * 64, row0);
+            for (int i = 0; i < ntiles; ++i) {
+                const int st = i % NS;
+                const uint32_t ph = (uint32_t)(i / NS) & 1u;
+                mbar_wait(&kv_empty[st], ph ^ 1u);
+                mbar_arrive_expect_tx(&kv_full[st], (uint32_t)tile_bytes);
+                for (int kc = 0; kc < kchunks; ++kc)
+                    tma_load_2d(&tm_queue, &kv_full[st], v_s + (size_t)st * tile_bytes + kc * kSlab, kc * 64,
+                                (t0 + i) * kDqBN);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer
+            const uint32_t idesc_s = make_idesc_bf16(128, kDqBN, 0, 0);            // S = q . tile^T  (both K-major)
+            const uint32_t idesc_o = make_idesc_bf16(128, (uint32_t)a.C, 0, 1);    // O += P . tile   (B MN-major)
+            mbar_wait(qfull, 0);
+            tc_fence_after();
+            auto issue_s = [&](int i) {
+                const int st = i % NS;
+                const int b = i & 1;
+                mbar_wait(&kv_full[st], (uint32_t)(i / NS) & 1u);
+                mbar_wait(&s_empty[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t q_addr = smem_u32(q_s), v_addr = smem_u32(v_s + (size_t)st * tile_bytes);
+                for (int kc = 0; kc < kchunks; ++kc) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        umma_ss<1>(tmem_base + (uint32_t)(b * kDqBN),
+                                   make_sw128_desc(q_addr + kc * kSlab + k * 32, 0, 1024),
+                                   make_sw128_desc(v_addr + kc * kSlab + k * 32, 0, 1024), idesc_s,
+                                   (uint32_t)((kc | k) != 0));
+                    }
+                }
+                umma_commit<1>(&s_full[b]);
+            };
+            if (ntiles > 0) issue_s(0);
+            for (int i = 0; i < ntiles; ++i) {
+                if (i + 1 < ntiles) issue_s(i + 1);
+                const int st = i % NS;
+                mbar_wait(p_full, (uint32_t)i & 1u);
+                tc_fence_after();
+                const uint32_t p_addr = smem_u32(p_s), v_addr = smem_u32(v_s + (size_t)st * tile_bytes);
+#pragma unroll
+                for (int kk = 0; kk < kDqBN / 16; ++kk) {
+                    // A = P[:, 16kk .. 16kk+16) (K-major slab kk/4, 32-byte step kk%4)
+                    // B = tile rows [16kk, 16kk+16) x C  (MN-major: 64-element chunks LBO = slab apart,
+                    //     8-row groups SBO = 1024 B apart)
+                    umma_ss<1>(tmem_base + kOCol,
+                               make_sw128_desc(p_addr + (kk >> 2) * kSlab + (kk & 3) * 32, 0, 1024),
+                               make_sw128_desc(v_addr + kk * 2048, kSlab, 1024), idesc_o,
+                               (uint32_t)((i | kk) != 0));
+                }
+                umma_commit<1>(&kv_empty[st]);
+                umma_commit<1>(p_empty);
+            }
+            umma_commit<1>(o_full);
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------- softmax warps (8) + O epilogue
+        const int quarter = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int row_local = quarter * 32 + lane;
+        const int grow = row0 + row_local;
+        const float scale2 = a.inv_T * kLog2e;
+        const float lse2 = (grow < a.N) ? a.lse[grow] * kLog2e : 0.f;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        uint8_t* p_row = p_s + half * kSlab + row_local * 128;     // this thread's 128-byte P row (64 cols)
+        const int sw = row_local & 7;
+        for (int i = 0; i < ntiles; ++i) {
+            const int b = i & 1;
+            mbar_wait(&s_full[b], (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            uint32_t packed[32];       // 64 bf16
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t r[32];
+                tmem_ld32(lane_base + (uint32_t)(b * kDqBN + half * 64 + ch * 32), r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float e0 = ex2(fmaf(__uint_as_float(r[j]), scale2, -lse2));
+                    float e1 = ex2(fmaf(__uint_as_float(r[j + 1]), scale2, -lse2));
+                    __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
+                    packed[ch * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&h);
+                }
+            }
+            // S buffer b may now be overwritten by S(i+2)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[b]);
+            // P smem is free once PV(i-1) has completed
+            mbar_wait(p_empty, ((uint32_t)i & 1u) ^ 1u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                uint4 v = make_uint4(packed[u * 4], packed[u * 4 + 1], packed[u * 4 + 2], packed[u * 4 + 3]);
+                *reinterpret_cast<uint4*>(p_row + ((u ^ sw) << 4)) = v;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        // O epilogue: each thread stores its row's C/2 columns of the slice partial
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        const int ccols = a.C >> 1;
+        float* orow = a.part_o + ((size_t)slice * a.n_pad + grow) * a.C + half * ccols;
+        for (int c = 0; c < ccols; c += 32) {
+            uint32_t r[32];
+            if (ntiles > 0) {
+                tmem_ld32(lane_base + kOCol + (uint32_t)(half * ccols + c), r);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<uint4*>(orow + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
+// =====================================================================================
+// Host side
+// =====================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || p == nullptr)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// [rows, C] bf16 row-major tensor, box = [box_rows, 64 elements], 128B swizzle, OOB -> zeros.
+static bool make_tmap(CUtensorMap* m, const void* base, int rows, int C, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return false; }
+    return true;
+}
+
+template <typename Kern, typename Args>
+static cudaError_t launch_cluster(Kern kern, int grid, int threads, int smem, int cluster, cudaStream_t stream,
+                                  const CUtensorMap& a, const CUtensorMap& b, const Args& args) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a, b, args);
+}
+
+cudaError_t launch_nce_tc(NceTcParams& p, const NceWorkspace& ws, cudaStream_t stream) {
+    if (p.C % 64 != 0 || p.C < 64 || p.C > 256 || p.N < 1 || p.K < 1) return cudaErrorNotSupported;
+    const int G = p.cta_group;
+    const int kchunks = p.C / 64;
+    const int mblks = (p.N + 128 * G - 1) / (128 * G);
+    const int clusters_avail = p.num_sms / G;
+    if (mblks > clusters_avail) return cudaErrorNotSupported;
+    const int num_tiles = (p.K + kStatsBN - 1) / kStatsBN;
+    int slices = clusters_avail / mblks;
+    if (slices > num_tiles) slices = num_tiles;
+    const int n_pad = mblks * G * 128;
+    if ((size_t)slices * n_pad > (size_t)kMaxCtas * kRowsPerCta) return cudaErrorNotSupported;
+    p.slices = slices;
+    p.n_pad = n_pad;
+
+    CUtensorMap tm_q, tm_queue;
+    if (!make_tmap(&tm_q, p.q_bf16, p.N, p.C, 128)) return cudaErrorUnknown;
+    if (!make_tmap(&tm_queue, p.queue, p.K, p.C, kStatsBN / G)) return cudaErrorUnknown;
+
+    const int stage_bytes = (kStatsBN / G) * 128;
+    const int fixed = kchunks * kSlab + 4096;     // q tile + barriers/red_s
+    int stages = (kSmemBudget - fixed) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) return cudaErrorNotSupported;
+    const int smem = fixed + stages * stage_bytes + 1024;
+
+    StatsArgs a;
+    a.N = p.N; a.C = p.C; a.K = p.K;
+    a.mblks = mblks; a.slices = slices; a.n_pad = n_pad; a.num_tiles = num_tiles; a.stages = stages;
+    a.inv_T = p.inv_T;
+    a.logits = p.logits;
+    a.part_ms = ws.part_ms;
+    const int grid = mblks * slices * G;
+    if (G == 2) return launch_cluster(nce_stats_kernel<2>, grid, kStatsThreads, smem, 2, stream, tm_q, tm_queue, a);
+    return launch_cluster(nce_stats_kernel<1>, grid, kStatsThreads, smem, 1, stream, tm_q, tm_queue, a);
+}
+
+cudaError_t launch_nce_dq_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* queue, int N, int C, int K,
+                             float inv_T, const float* lse, int num_sms, int* slices_out, int* n_pad_out,
+                             const NceWorkspace& ws, cudaStream_t stream) {
+    if (C % 64 != 0 || C < 64 || C > 256) return cudaErrorNotSupported;
+    const int kchunks = C / 64;
+    const int mblks = (N + 127) / 128;
+    if (mblks > num_sms) return cudaErrorNotSupported;
+    const int num_tiles = (K + kDqBN - 1) / kDqBN;
+    int slices = num_sms / mblks;
+    if (slices > num_tiles) slices = num_tiles;
+    const int n_pad = mblks * 128;
+    if ((size_t)slices * n_pad > (size_t)kMaxCtas * kRowsPerCta) return cudaErrorNotSupported;
+    *slices_out = slices;
+    *n_pad_out = n_pad;
+
+    CUtensorMap tm_q, tm_queue;
+    if (!make_tmap(&tm_q, q_bf16, N, C, 128)) return cudaErrorUnknown;
+    if (!make_tmap(&tm_queue, queue, K, C, kDqBN)) return cudaErrorUnknown;
+
+    const int tile_bytes = kchunks * kSlab;
+    const int fixed = tile_bytes + 2 * kSlab + 1024;      // q + P + barriers
+    int stages = (kSmemBudget - fixed) / tile_bytes;
+    if (stages > 4) stages = 4;
+    if (stages < 2) return cudaErrorNotSupported;
+    const int smem = fixed + stages * tile_bytes + 1024;
+
+    DqArgs a;
+    a.N = N; a.C = C; a.K = K;
+    a.mblks = mblks; a.slices = slices; a.n_pad = n_pad; a.num_tiles = num_tiles; a.stages = stages;
+    a.inv_T = inv_T;
+    a.lse = lse;
+    a.part_o = ws.part_o;
+    return launch_cluster(nce_dq_kernel, mblks * slices, kDqThreads, smem, 1, stream, tm_q, tm_queue, a);
+}
+
+}  // namespace moco

@@ -1,0 +1,331 @@
+// Support kernels of the InfoNCE head: prep (positive logit + bf16 cast of q),
+// the cross-slice combine (lse / loss / prob / dq), the generic CUDA-core
+// row kernel (any shape; also the on-GPU cross-check of the tcgen05 kernels) and
+// the dense-gradient backward of the compatibility API.
+//
+// Reference semantics: moco/NCE/Contrast.py:20-27, moco/NCE/NCECriterion.py:11-13,
+// train.py:264,273 (see include/moco_b200.h).
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace moco {
+
+__device__ __forceinline__ float load_as_float(const void* p, int dtype, size_t idx) {
+    return dtype == 0 ? static_cast<const float*>(p)[idx]
+                      : __bfloat162float(static_cast<const __nv_bfloat16*>(p)[idx]);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Deterministic mean over rows by the last block to finish (fixed summation order).
+__device__ void finish_mean(unsigned int* counter, int N, const float* loss_rows, const float* prob_rows,
+                            float* loss_prob) {
+    __shared__ float s_red[2][32];
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int t = atomicAdd(counter, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float a = 0.f, b = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        a += __ldcg(loss_rows + i);
+        b += __ldcg(prob_rows + i);
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0) { s_red[0][w] = a; s_red[1][w] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float sa = 0.f, sb = 0.f;
+        for (int i = 0; i < nw; ++i) { sa += s_red[0][i]; sb += s_red[1][i]; }
+        loss_prob[0] = sa / (float)N;
+        loss_prob[1] = sb / (float)N;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// prep: lpos[i] = <q_i, k_i> (fp32), q_bf16 = bf16(q) when q is fp32, zero counters.
+// One warp per row.
+// ---------------------------------------------------------------------------
+__global__ void prep_kernel(const void* __restrict__ q, const void* __restrict__ k, int dtype, int N, int C,
+                            float* __restrict__ lpos, __nv_bfloat16* __restrict__ q_bf16,
+                            unsigned int* __restrict__ counters) {
+    if (blockIdx.x == 0 && threadIdx.x < 4) counters[threadIdx.x] = 0u;
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= N) return;
+    int lane = threadIdx.x & 31;
+    float acc = 0.f;
+    size_t base = (size_t)row * C;
+    for (int c = lane; c < C; c += 32) {
+        float qv = load_as_float(q, dtype, base + c);
+        float kv = load_as_float(k, dtype, base + c);
+        acc = fmaf(qv, kv, acc);
+        if (dtype == 0) q_bf16[base + c] = __float2bfloat16_rn(qv);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) lpos[row] = acc;
+}
+
+cudaError_t launch_prep(const void* q, const void* k, int qk_dtype, int N, int C, const NceWorkspace& ws,
+                        cudaStream_t stream) {
+    int rows_per_block = 4;
+    prep_kernel<<<(N + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, stream>>>(
+        q, k, qk_dtype, N, C, ws.lpos, ws.q_bf16, ws.counters);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// combine: merge the per-slice (max, sum[, O]) partials of the tcgen05 kernel.
+// One block per q row.
+// ---------------------------------------------------------------------------
+__global__ void combine_kernel(int N, int C, int K, int slices, int n_pad, float inv_T,
+                               const float* __restrict__ lpos, const float2* __restrict__ part_ms,
+                               float* __restrict__ logits,
+                               float* __restrict__ lse, float* __restrict__ loss_rows,
+                               float* __restrict__ prob_rows, float* __restrict__ loss_prob,
+                               unsigned int* __restrict__ counters) {
+    const int i = blockIdx.x;
+    const float scale2 = inv_T * kLog2e;
+    const float x0 = lpos[i] * scale2;             // positive logit, log2 domain
+    if (threadIdx.x < 32) {
+        int lane = threadIdx.x;
+        float m = x0;
+        for (int s = lane; s < slices; s += 32) m = fmaxf(m, part_ms[(size_t)s * n_pad + i].x);
+        m = warp_max(m);
+        float l = 0.f;
+        for (int s = lane; s < slices; s += 32) {
+            float2 ms = part_ms[(size_t)s * n_pad + i];
+            l += ms.y * ex2(ms.x - m);             // ms.x == -inf (empty slice) -> 0
+        }
+        l = warp_sum(l);
+        l += ex2(x0 - m);
+        float lse2 = m + log2f(l);
+        if (lane == 0) {
+            float lse_nat = lse2 * kLn2;
+            float x0n = lpos[i] * inv_T;
+            float prob = exp2f(x0 - lse2);
+            lse[i] = lse_nat;
+            loss_rows[i] = lse_nat - x0n;
+            prob_rows[i] = prob;
+            if (logits) logits[(size_t)i * (K + 1)] = x0n;
+        }
+    }
+    finish_mean(counters + 0, N, loss_rows, prob_rows, loss_prob);
+}
+
+cudaError_t launch_combine(int N, int C, int slices, int n_pad, float inv_T, float* logits, int K, float* lse,
+                           float* loss_rows, float* prob_rows, float* loss_prob, const NceWorkspace& ws,
+                           cudaStream_t stream) {
+    combine_kernel<<<N, 32, 0, stream>>>(N, C, K, slices, n_pad, inv_T, ws.lpos, ws.part_ms, logits, lse,
+                                         loss_rows, prob_rows, loss_prob, ws.counters);
+    return cudaGetLastError();
+}
+
+// dq_i = inv_T / N * ( sum_slices O_s[i] + (prob_i - 1) k_i )   -- fixed summation order.
+__global__ void dq_reduce_kernel(int N, int C, int slices, int n_pad, float inv_T, const void* __restrict__ k,
+                                 int k_dtype, const float* __restrict__ part_o,
+                                 const float* __restrict__ prob_rows, float* __restrict__ dq) {
+    const int i = blockIdx.x;
+    const float gscale = inv_T / (float)N;
+    const float pm1 = prob_rows[i] - 1.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int s = 0; s < slices; ++s) acc += part_o[((size_t)s * n_pad + i) * C + c];
+        float kv = load_as_float(k, k_dtype, (size_t)i * C + c);
+        dq[(size_t)i * C + c] = gscale * (acc + pm1 * kv);
+    }
+}
+
+cudaError_t launch_dq_reduce(int N, int C, int slices, int n_pad, float inv_T, const void* k, int k_dtype,
+                             const float* prob_rows, float* dq, const NceWorkspace& ws, cudaStream_t stream) {
+    int threads = C >= 256 ? 256 : (C + 31) / 32 * 32;
+    dq_reduce_kernel<<<N, threads, 0, stream>>>(N, C, slices, n_pad, inv_T, k, k_dtype, ws.part_o, prob_rows, dq);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Generic CUDA-core path: one block per q row, any (N, C <= 1024, K).
+// ---------------------------------------------------------------------------
+constexpr int kSimtThreads = 256;
+constexpr int kSimtMaxC = 1024;
+
+__device__ __forceinline__ float dot_row(const float* __restrict__ qs, const __nv_bfloat16* __restrict__ row, int C) {
+    float acc = 0.f;
+    if ((C & 7) == 0) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(row);
+        for (int v = 0; v < (C >> 3); ++v) {
+            uint4 u = __ldg(r4 + v);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float2 f = __bfloat1622float2(h[e]);
+                acc = fmaf(qs[v * 8 + e * 2], f.x, acc);
+                acc = fmaf(qs[v * 8 + e * 2 + 1], f.y, acc);
+            }
+        }
+    } else {
+        for (int c = 0; c < C; ++c) acc = fmaf(qs[c], __bfloat162float(row[c]), acc);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(kSimtThreads)
+simt_rows_kernel(const __nv_bfloat16* __restrict__ q_bf16, const void* __restrict__ k, int k_dtype,
+                 const __nv_bfloat16* __restrict__ queue, int N, int C, int K, float inv_T,
+                 const float* __restrict__ lpos, float* __restrict__ logits, float* __restrict__ lse,
+                 float* __restrict__ loss_rows, float* __restrict__ prob_rows, float* __restrict__ loss_prob,
+                 float* __restrict__ dq, unsigned int* __restrict__ counters) {
+    __shared__ float qs[kSimtMaxC];
+    __shared__ float ps[kSimtThreads];
+    __shared__ float red_m[kSimtThreads / 32], red_s[kSimtThreads / 32];
+    __shared__ float s_bcast[2];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const float scale2 = inv_T * kLog2e;
+    for (int c = tid; c < C; c += kSimtThreads) qs[c] = __bfloat162float(q_bf16[(size_t)i * C + c]);
+    __syncthreads();
+    const float x0 = lpos[i] * scale2;
+    // pass 1: logits (optional store) + online (max, sum) in the log2 domain
+    float m = -INFINITY, s = 0.f;
+    for (int j = tid; j < K; j += kSimtThreads) {
+        float d = dot_row(qs, queue + (size_t)j * C, C);
+        if (logits) logits[(size_t)i * (K + 1) + 1 + j] = d * inv_T;
+        float x = d * scale2;
+        if (x > m) { s *= ex2(m - x); m = x; }
+        s += ex2(x - m);
+    }
+    // block combine of (m, s)
+    float wm = warp_max(m);
+    float ws_ = warp_sum(m == -INFINITY ? 0.f : s * ex2(m - wm));
+    if ((tid & 31) == 0) { red_m[tid >> 5] = wm; red_s[tid >> 5] = ws_; }
+    __syncthreads();
+    if (tid == 0) {
+        float M = x0;
+        for (int w = 0; w < kSimtThreads / 32; ++w) M = fmaxf(M, red_m[w]);
+        float L = ex2(x0 - M);
+        for (int w = 0; w < kSimtThreads / 32; ++w)
+            if (red_m[w] != -INFINITY) L += red_s[w] * ex2(red_m[w] - M);
+        float lse2 = M + log2f(L);
+        float lse_nat = lse2 * kLn2, x0n = lpos[i] * inv_T, prob = exp2f(x0 - lse2);
+        lse[i] = lse_nat;
+        loss_rows[i] = lse_nat - x0n;
+        prob_rows[i] = prob;
+        if (logits) logits[(size_t)i * (K + 1)] = x0n;
+        s_bcast[0] = lse2;
+        s_bcast[1] = prob;
+    }
+    __syncthreads();
+    if (dq) {
+        const float lse2 = s_bcast[0], prob = s_bcast[1];
+        float acc[kSimtMaxC / kSimtThreads];
+#pragma unroll
+        for (int u = 0; u < kSimtMaxC / kSimtThreads; ++u) acc[u] = 0.f;
+        for (int jb = 0; jb < K; jb += kSimtThreads) {
+            int j = jb + tid;
+            ps[tid] = (j < K) ? ex2(dot_row(qs, queue + (size_t)j * C, C) * scale2 - lse2) : 0.f;
+            __syncthreads();
+            int jn = min(kSimtThreads, K - jb);
+#pragma unroll
+            for (int u = 0; u < kSimtMaxC / kSimtThreads; ++u) {
+                int c = tid + u * kSimtThreads;
+                if (c < C) {
+                    float a = acc[u];
+                    for (int jj = 0; jj < jn; ++jj)
+                        a = fmaf(ps[jj], __bfloat162float(queue[(size_t)(jb + jj) * C + c]), a);
+                    acc[u] = a;
+                }
+            }
+            __syncthreads();
+        }
+        const float gscale = inv_T / (float)N;
+#pragma unroll
+        for (int u = 0; u < kSimtMaxC / kSimtThreads; ++u) {
+            int c = tid + u * kSimtThreads;
+            if (c < C) {
+                float kv = load_as_float(k, k_dtype, (size_t)i * C + c);
+                dq[(size_t)i * C + c] = gscale * (acc[u] + (prob - 1.f) * kv);
+            }
+        }
+    }
+    finish_mean(counters + 0, N, loss_rows, prob_rows, loss_prob);
+}
+
+cudaError_t launch_simt_rows(const __nv_bfloat16* q_bf16, const void* k, int k_dtype, const __nv_bfloat16* queue,
+                             int N, int C, int K, float inv_T, float* logits, float* lse, float* loss_rows,
+                             float* prob_rows, float* loss_prob, float* dq, const NceWorkspace& ws,
+                             cudaStream_t stream) {
+    if (C > kSimtMaxC) return cudaErrorNotSupported;
+    simt_rows_kernel<<<N, kSimtThreads, 0, stream>>>(q_bf16, k, k_dtype, queue, N, C, K, inv_T, ws.lpos, logits,
+                                                     lse, loss_rows, prob_rows, loss_prob, dq, ws.counters);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Dense-gradient backward (compat API):  dq_i = inv_T (g_i0 k_i + sum_j g_i,1+j queue_j)
+// kDenseRows q rows per block so the queue is streamed N / kDenseRows times.
+// ---------------------------------------------------------------------------
+constexpr int kDenseRows = 8;
+constexpr int kDenseChunk = 128;
+
+__global__ void __launch_bounds__(256)
+bwd_dense_kernel(const float* __restrict__ g, const void* __restrict__ k, int k_dtype,
+                 const __nv_bfloat16* __restrict__ queue, int N, int C, int K, float inv_T,
+                 float* __restrict__ dq) {
+    __shared__ float gs[kDenseRows][kDenseChunk];
+    const int i0 = blockIdx.x * kDenseRows;
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    float acc[kDenseRows];
+#pragma unroll
+    for (int r = 0; r < kDenseRows; ++r) acc[r] = 0.f;
+    for (int jb = 0; jb < K; jb += kDenseChunk) {
+        for (int e = threadIdx.x; e < kDenseRows * kDenseChunk; e += blockDim.x) {
+            int r = e / kDenseChunk, jj = e % kDenseChunk;
+            int i = i0 + r, j = jb + jj;
+            gs[r][jj] = (i < N && j < K) ? g[(size_t)i * (K + 1) + 1 + j] : 0.f;
+        }
+        __syncthreads();
+        if (c < C) {
+            int jn = min(kDenseChunk, K - jb);
+            for (int jj = 0; jj < jn; ++jj) {
+                float v = __bfloat162float(queue[(size_t)(jb + jj) * C + c]);
+#pragma unroll
+                for (int r = 0; r < kDenseRows; ++r) acc[r] = fmaf(gs[r][jj], v, acc[r]);
+            }
+        }
+        __syncthreads();
+    }
+    if (c < C) {
+#pragma unroll
+        for (int r = 0; r < kDenseRows; ++r) {
+            int i = i0 + r;
+            if (i < N) {
+                float kv = load_as_float(k, k_dtype, (size_t)i * C + c);
+                dq[(size_t)i * C + c] = inv_T * (g[(size_t)i * (K + 1)] * kv + acc[r]);
+            }
+        }
+    }
+}
+
+cudaError_t launch_bwd_dense(const float* g, const void* k, int k_dtype, const __nv_bfloat16* queue, int N, int C,
+                             int K, float inv_T, float* dq, cudaStream_t stream) {
+    int threads = C >= 256 ? 256 : ((C + 31) / 32 * 32);
+    dim3 grid((N + kDenseRows - 1) / kDenseRows, (C + threads - 1) / threads);
+    bwd_dense_kernel<<<grid, threads, 0, stream>>>(g, k, k_dtype, queue, N, C, K, inv_T, dq);
+    return cudaGetLastError();
+}
+
+}  // namespace moco

@@ -1,0 +1,261 @@
+// FIFO queue enqueue (moco/NCE/Contrast.py:29-34), fp32->bf16 cast, and the
+// ShuffleBN peer-memory row gather (moco/util.py:47-58,69-93) with its
+// cross-GPU signal barrier.  All HBM/NVLink-bound byte movers: 16-byte vector
+// accesses, bulk-async (TMA) copies for large rows, grids sized from the SM count.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace moco {
+
+// ---------------------------------------------------------------------------
+// enqueue: queue[(index + i) mod K] = k_all[i]; one thread per 8 elements.
+// ---------------------------------------------------------------------------
+__global__ void enqueue_kernel(__nv_bfloat16* __restrict__ qb, float* __restrict__ qf,
+                               const void* __restrict__ k_all, int k_dtype, int n_all, int C, long long K,
+                               long long index) {
+    const int vec_per_row = C >> 3;
+    const long long total = (long long)n_all * vec_per_row;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(t / vec_per_row), v = (int)(t % vec_per_row);
+        long long dst = (index + i) % K;
+        float f[8];
+        if (k_dtype == 0) {
+            const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(k_all) + (size_t)i * C) + v * 2;
+            float4 a = src[0], b = src[1];
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        } else {
+            uint4 u = *(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(k_all) + (size_t)i * C) + v);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { float2 x = __bfloat1622float2(h[e]); f[2 * e] = x.x; f[2 * e + 1] = x.y; }
+        }
+        uint4 packed;
+        __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(&packed);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ph[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+        *(reinterpret_cast<uint4*>(qb + (size_t)dst * C) + v) = packed;
+        if (qf) {
+            float4* d = reinterpret_cast<float4*>(qf + (size_t)dst * C) + v * 2;
+            d[0] = make_float4(f[0], f[1], f[2], f[3]);
+            d[1] = make_float4(f[4], f[5], f[6], f[7]);
+        }
+    }
+}
+
+// scalar variant for C % 8 != 0
+__global__ void enqueue_scalar_kernel(__nv_bfloat16* __restrict__ qb, float* __restrict__ qf,
+                                      const void* __restrict__ k_all, int k_dtype, int n_all, int C, long long K,
+                                      long long index) {
+    const long long total = (long long)n_all * C;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(t / C), c = (int)(t % C);
+        long long dst = (index + i) % K;
+        float f = k_dtype == 0 ? static_cast<const float*>(k_all)[t]
+                               : __bfloat162float(static_cast<const __nv_bfloat16*>(k_all)[t]);
+        qb[(size_t)dst * C + c] = __float2bfloat16_rn(f);
+        if (qf) qf[(size_t)dst * C + c] = f;
+    }
+}
+
+cudaError_t launch_enqueue(__nv_bfloat16* queue_bf16, float* queue_f32, const void* k_all, int k_dtype, int n_all,
+                           int C, int64_t K, int64_t index, cudaStream_t stream) {
+    if (n_all == 0) return cudaSuccess;
+    if ((C & 7) == 0) {
+        long long total = (long long)n_all * (C >> 3);
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        enqueue_kernel<<<blocks, 256, 0, stream>>>(queue_bf16, queue_f32, k_all, k_dtype, n_all, C, K, index);
+    } else {
+        long long total = (long long)n_all * C;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        enqueue_scalar_kernel<<<blocks, 256, 0, stream>>>(queue_bf16, queue_f32, k_all, k_dtype, n_all, C, K, index);
+    }
+    return cudaGetLastError();
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t n4 = n >> 2;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += stride) {
+        float4 a = reinterpret_cast<const float4*>(src)[t];
+        __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&lo);
+        u.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(dst)[t] = u;
+    }
+    for (size_t t = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+        dst[t] = __float2bfloat16_rn(src[t]);
+}
+
+cudaError_t launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    size_t blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks == 0) blocks = 1;
+    f32_to_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(src, dst, n);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// ShuffleBN gather.
+// ---------------------------------------------------------------------------
+constexpr int kMaxWorld = 16;
+struct PeerTable { const char* base[kMaxWorld]; };
+
+// Small rows (feature vectors): one warp per destination row, 16-byte lanes.
+__global__ void gather_small_kernel(PeerTable peers, int rows_per_rank, const int64_t* __restrict__ src_rows,
+                                    int n_rows, int vec_per_row, uint4* __restrict__ dst) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    int lane = threadIdx.x & 31;
+    long long g = src_rows[row];
+    const uint4* src = reinterpret_cast<const uint4*>(peers.base[g / rows_per_rank]) + (size_t)(g % rows_per_rank) * vec_per_row;
+    uint4* d = dst + (size_t)row * vec_per_row;
+    for (int v = lane; v < vec_per_row; v += 32) d[v] = src[v];
+}
+
+// Large rows (images): a persistent grid of CTAs walks (row, chunk) work items.  Each item is a
+// kChunk-byte bulk-async copy peer HBM -> smem (cp.async.bulk, completes on an mbarrier) followed by a
+// bulk store smem -> local HBM, kStages deep, issued by ONE thread per CTA: the copy engines move the
+// bytes over NVLink while the SM's warps stay free for a concurrently running kernel.
+constexpr int kChunk = 32 * 1024;
+constexpr int kStages = 4;
+
+__global__ void __launch_bounds__(32)
+gather_bulk_kernel(PeerTable peers, int rows_per_rank, const int64_t* __restrict__ src_rows, int n_rows,
+                   unsigned long long row_bytes, char* __restrict__ dst) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full[kStages];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    const unsigned long long chunks_per_row = (row_bytes + kChunk - 1) / kChunk;
+    const unsigned long long total = chunks_per_row * (unsigned long long)n_rows;
+    // items owned by this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    unsigned long long issue = blockIdx.x, drain = blockIdx.x;
+    int n_issued = 0, n_drained = 0;
+    auto item = [&](unsigned long long it, const char*& s, char*& d, uint32_t& bytes) {
+        unsigned long long row = it / chunks_per_row, ch = it % chunks_per_row;
+        long long g = src_rows[row];
+        unsigned long long off = ch * kChunk;
+        bytes = (uint32_t)min((unsigned long long)kChunk, row_bytes - off);
+        s = peers.base[g / rows_per_rank] + (unsigned long long)(g % rows_per_rank) * row_bytes + off;
+        d = dst + row * row_bytes + off;
+    };
+    while (drain < total) {
+        // keep kStages loads in flight
+        while (issue < total && n_issued - n_drained < kStages) {
+            int st = n_issued % kStages;
+            if (n_issued >= kStages) {
+                // the bulk store that last read this stage must have finished reading smem
+                // (in steady state exactly that store is the oldest uncommitted-complete group)
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            const char* s; char* d; uint32_t bytes;
+            item(issue, s, d, bytes);
+            mbar_arrive_expect_tx(&full[st], bytes);
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(smem_u32(smem + (size_t)st * kChunk)), "l"(s), "r"(bytes), "r"(smem_u32(&full[st])) : "memory");
+            issue += gridDim.x;
+            ++n_issued;
+        }
+        int st = n_drained % kStages;
+        mbar_wait(&full[st], (n_drained / kStages) & 1);
+        const char* s; char* d; uint32_t bytes;
+        item(drain, s, d, bytes);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(d), "r"(smem_u32(smem + (size_t)st * kChunk)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        drain += gridDim.x;
+        ++n_drained;
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// Large rows, plain 16-byte LDG/STG path (fallback / comparison for the bulk-async kernel).
+// grid = (segments per row, rows); each thread keeps 4 independent 16-byte loads in flight.
+__global__ void __launch_bounds__(256)
+gather_ldg_kernel(PeerTable peers, int rows_per_rank, const int64_t* __restrict__ src_rows, int n_rows,
+                  unsigned long long vec_per_row, uint4* __restrict__ dst) {
+    int row = blockIdx.y;
+    long long g = src_rows[row];
+    const uint4* src = reinterpret_cast<const uint4*>(peers.base[g / rows_per_rank]) + (unsigned long long)(g % rows_per_rank) * vec_per_row;
+    uint4* d = dst + (unsigned long long)row * vec_per_row;
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; v + 3 * stride < vec_per_row; v += 4 * stride) {
+        uint4 a = src[v], b = src[v + stride], c = src[v + 2 * stride], e = src[v + 3 * stride];
+        d[v] = a; d[v + stride] = b; d[v + 2 * stride] = c; d[v + 3 * stride] = e;
+    }
+    for (; v < vec_per_row; v += stride) d[v] = src[v];
+}
+
+cudaError_t launch_gather(const void* const* peers_host, int world, int rows_per_rank, const int64_t* src_rows,
+                          int n_rows, size_t row_bytes, void* dst, int flags, cudaStream_t stream) {
+    if (n_rows == 0) return cudaSuccess;
+    if (world > kMaxWorld) return cudaErrorInvalidValue;
+    PeerTable t;
+    for (int i = 0; i < kMaxWorld; ++i) t.base[i] = i < world ? static_cast<const char*>(peers_host[i]) : nullptr;
+    if (row_bytes >= (size_t)kChunk / 2 && (flags & 1)) {
+        unsigned long long vec = row_bytes / 16;
+        int gx = (int)((vec + 256 * 4 - 1) / (256 * 4));
+        if (gx > 8) gx = 8;
+        gather_ldg_kernel<<<dim3(gx, n_rows), 256, 0, stream>>>(t, rows_per_rank, src_rows, n_rows, vec,
+                                                                static_cast<uint4*>(dst));
+    } else if (row_bytes >= (size_t)kChunk / 2) {
+        static bool attr_set = false;
+        const int smem = kStages * kChunk;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        size_t chunks = (row_bytes + kChunk - 1) / kChunk * (size_t)n_rows;
+        int grid = (int)(chunks < 148 ? chunks : 148);
+        gather_bulk_kernel<<<grid, 32, smem, stream>>>(t, rows_per_rank, src_rows, n_rows, row_bytes,
+                                                       static_cast<char*>(dst));
+    } else {
+        int vec = (int)(row_bytes / 16);
+        int rows_per_block = 8;
+        gather_small_kernel<<<(n_rows + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, stream>>>(
+            t, rows_per_rank, src_rows, n_rows, vec, static_cast<uint4*>(dst));
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Signal barrier: slot[writer] of every peer's pad := epoch (release, system scope), then wait for
+// all slots of the own pad (acquire).  Bounded spin.
+// ---------------------------------------------------------------------------
+struct PadTable { uint32_t* pad[kMaxWorld]; };
+
+__global__ void signal_barrier_kernel(PadTable pads, int world, int rank, uint32_t epoch) {
+    int p = threadIdx.x;
+    if (p >= world) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pads.pad[p] + rank), "r"(epoch) : "memory");
+    uint32_t v, spins = 0;
+    const uint32_t* mine = pads.pad[rank] + p;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if (++spins > (1u << 28)) __trap();
+    } while ((int32_t)(v - epoch) < 0);
+}
+
+cudaError_t launch_signal_barrier(void* const* pads_host, int world, int rank, uint32_t epoch, cudaStream_t stream) {
+    if (world > kMaxWorld) return cudaErrorInvalidValue;
+    PadTable t;
+    for (int i = 0; i < kMaxWorld; ++i) t.pad[i] = i < world ? static_cast<uint32_t*>(pads_host[i]) : nullptr;
+    signal_barrier_kernel<<<1, 32, 0, stream>>>(t, world, rank, epoch);
+    return cudaGetLastError();
+}
+
+}  // namespace moco

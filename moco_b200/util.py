@@ -1,0 +1,243 @@
+"""ShuffleBN and helpers -- drop-in for the hot-path part of ``moco/util.py`` (bl0/moco).
+
+Same public names and semantics as the reference (``util.py:47-111``):
+``dist_collect``, ``DistributedShufle.{forward_shuffle, backward_shuffle,
+get_local_id, get_shuffle_ids}``; plus ``set_bn_train`` / ``moment_update``
+(``util.py:114-127``) which the training step needs.
+
+B200-native design: the reference all_gathers every rank's whole batch (W x the
+bytes it needs, plus a zero-fill and a cat of the same size, util.py:55-58) and
+then indexes it.  Here each rank publishes its batch in a peer-mapped staging
+buffer and every rank PULLS exactly the rows its slice of the permutation names,
+straight over NVLink/NVSwitch, with one kernel (``moco_shuffle_gather``): the
+permutation is the address computation.  Peers are synchronised with a
+stream-ordered signal-pad barrier (``moco_signal_barrier``); staging buffers are
+double-buffered so one barrier per shuffle suffices.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def _world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+# ---------------------------------------------------------------------------
+# permutation ids (host side; bit-exact with the reference)
+# ---------------------------------------------------------------------------
+_IDS_CACHE: Dict[Tuple[int, int, str], Tuple[torch.Tensor, torch.Tensor]] = {}
+
+
+def shuffle_ids_cpu(bsz: int, epoch: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """forward/backward permutation exactly as ``util.py:99-111`` computes them
+    (``torch.manual_seed(epoch); torch.randperm(bsz)`` on the CPU generator), but
+    drawn from a PRIVATE generator: the reference re-seeds the global RNG on every
+    training step as a side effect; we do not."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(epoch)
+    forward_inds = torch.randperm(bsz, generator=g).long()
+    backward_inds = torch.zeros(bsz, dtype=torch.long)
+    backward_inds.index_copy_(0, forward_inds, torch.arange(bsz, dtype=torch.long))
+    return forward_inds, backward_inds
+
+
+def plan_forward(forward_inds: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """Global source rows rank `rank` pulls in forward_shuffle (util.py:77-79,96-97)."""
+    n = forward_inds.shape[0] // world
+    return forward_inds[rank * n:(rank + 1) * n]
+
+
+# ---------------------------------------------------------------------------
+# peer-memory context
+# ---------------------------------------------------------------------------
+class _PeerBuffer:
+    """A cudaMalloc'ed buffer of this rank, mapped by every peer (CUDA IPC)."""
+
+    def __init__(self, nbytes: int, rank: int, world: int, group=None):
+        lib = _lib.load()
+        self.nbytes = nbytes
+        self.rank, self.world = rank, world
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(lib.moco_p2p_alloc(nbytes, ctypes.byref(ptr), handle), "moco_p2p_alloc")
+        self.local = ptr.value
+        self.ptrs = [None] * world
+        self.ptrs[rank] = self.local
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            for r in range(world):
+                if r == rank:
+                    continue
+                h = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+                p = ctypes.c_void_p()
+                _lib.check(lib.moco_p2p_open(h, ctypes.byref(p)), "moco_p2p_open")
+                self.ptrs[r] = p.value
+        self.table = (ctypes.c_void_p * world)(*self.ptrs)
+
+    def tensor(self, shape, dtype) -> torch.Tensor:
+        """View of the local buffer as a torch tensor (no copy)."""
+        numel = 1
+        for s in shape:
+            numel *= s
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        assert nbytes <= self.nbytes
+
+        class _Iface:
+            pass
+        obj = _Iface()
+        obj.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1",
+                                        "data": (self.local, False), "version": 2}
+        t = torch.as_tensor(obj, device=f"cuda:{torch.cuda.current_device()}")
+        return t.view(dtype).view(tuple(shape))
+
+
+class ShuffleContext:
+    """Per-process-group state of the P2P ShuffleBN: staging buffers (double-buffered), signal pad,
+    barrier epoch.  Created lazily on first use; every rank must call the shuffles in the same order."""
+
+    _instance: Optional["ShuffleContext"] = None
+
+    def __init__(self, group=None):
+        self.rank, self.world = _world()
+        self.group = group
+        self.pad = _PeerBuffer(4096, self.rank, self.world, group) if self.world > 1 else None
+        self.epoch = 0
+        self.staging: Dict[str, list] = {}
+        self.turn: Dict[str, int] = {}
+        self.gather_flags = _lib.GATHER_AUTO
+
+    @classmethod
+    def get(cls) -> "ShuffleContext":
+        rank, world = _world()
+        inst = cls._instance
+        if inst is None or inst.world != world or inst.rank != rank:
+            inst = cls._instance = ShuffleContext()
+        return inst
+
+    def _staging(self, kind: str, nbytes: int):
+        bufs = self.staging.get(kind)
+        if bufs is None or bufs[0].nbytes < nbytes:
+            # (re)allocation is collective: every rank sees the same sizes at the same call
+            bufs = [_PeerBuffer(nbytes, self.rank, self.world, self.group) for _ in range(2)]
+            self.staging[kind] = bufs
+            self.turn[kind] = 0
+        t = self.turn[kind]
+        self.turn[kind] = t ^ 1
+        return bufs[t]
+
+    def barrier(self):
+        lib = _lib.load()
+        self.epoch += 1
+        _lib.check(lib.moco_signal_barrier(self.pad.table, self.world, self.rank, self.epoch, _lib.cur_stream()),
+                   "moco_signal_barrier")
+
+    def gather(self, kind: str, x: torch.Tensor, src_rows: torch.Tensor) -> torch.Tensor:
+        """out[i] = (rank-major concatenation of every rank's x)[src_rows[i]]."""
+        lib = _lib.load()
+        _lib.require_cuda(x, src_rows)
+        x = x.contiguous()
+        n = x.shape[0]
+        row_bytes = x[0].numel() * x.element_size() if n else 0
+        if row_bytes % 16 != 0:
+            raise ValueError(f"moco_b200 shuffle: row size {row_bytes} B is not a multiple of 16")
+        out = torch.empty((src_rows.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        if self.world == 1:
+            table = (ctypes.c_void_p * 1)(x.data_ptr())
+        else:
+            buf = self._staging(kind, x.numel() * x.element_size())
+            stage = buf.tensor(x.shape, x.dtype)
+            if stage.data_ptr() != x.data_ptr():
+                stage.copy_(x)
+            self.barrier()           # every rank's staging buffer is complete and visible
+            table = buf.table
+        _lib.check(lib.moco_shuffle_gather(table, self.world, n, src_rows.data_ptr(), src_rows.shape[0],
+                                           row_bytes, out.data_ptr(), self.gather_flags, _lib.cur_stream()),
+                   "moco_shuffle_gather")
+        return out
+
+
+# ---------------------------------------------------------------------------
+# reference API
+# ---------------------------------------------------------------------------
+def dist_collect(x):
+    """collect all tensor from all GPUs (util.py:47-58): [mini_batch, ...] -> [mini_batch * W, ...],
+    rank-major.  Implemented as a P2P pull of every row (identity permutation)."""
+    rank, world = _world()
+    if world == 1:
+        return x.contiguous().clone()
+    n = x.shape[0]
+    rows = torch.arange(n * world, dtype=torch.long, device=x.device)
+    return ShuffleContext.get().gather("collect", x, rows)
+
+
+class DistributedShufle:
+    @staticmethod
+    def forward_shuffle(x, epoch):
+        """forward shuffle, return shuffled batch of x from all processes (util.py:69-79).
+        epoch is used as manual seed to make sure the shuffle id in all process is same."""
+        rank, world = _world()
+        forward_inds, backward_inds = DistributedShufle.get_shuffle_ids(x.shape[0] * world, epoch, x.device)
+        forward_inds_local = DistributedShufle.get_local_id(forward_inds)
+        return ShuffleContext.get().gather("fwd", x, forward_inds_local), backward_inds
+
+    @staticmethod
+    def backward_shuffle(x, backward_inds, return_local=True):
+        """backward shuffle, return data which have been shuffled back (util.py:81-93).
+        x is the shared data, should be local data.  if return_local, only return the local batch
+        data of x; otherwise, return collected all data on all process."""
+        x_all = ShuffleContext.get().gather("bwd", x, backward_inds)      # rank-major original order
+        if return_local:
+            rank, world = _world()
+            n = x.shape[0]
+            return x_all, x_all[rank * n:(rank + 1) * n]
+        return x_all
+
+    @staticmethod
+    def get_local_id(ids):
+        rank, world = _world()
+        return ids.chunk(world)[rank]
+
+    @staticmethod
+    def get_shuffle_ids(bsz, epoch, device=None):
+        """generate shuffle ids for ShuffleBN (util.py:99-111); cached per (bsz, epoch, device) --
+        the reference recomputes the same permutation (and three H2D copies) every step."""
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        key = (bsz, epoch, str(device))
+        hit = _IDS_CACHE.get(key)
+        if hit is None:
+            if len(_IDS_CACHE) > 64:
+                _IDS_CACHE.clear()
+            f, b = shuffle_ids_cpu(bsz, epoch)
+            hit = _IDS_CACHE[key] = (f.to(device), b.to(device))
+        return hit
+
+
+def set_bn_train(model):
+    """key encoder in eval() with BatchNorm layers in train() (util.py:114-121)."""
+    def set_bn_train_helper(m):
+        if m.__class__.__name__.find('BatchNorm') != -1:
+            m.train()
+
+    model.eval()
+    model.apply(set_bn_train_helper)
+
+
+@torch.no_grad()
+def moment_update(model, model_ema, m):
+    """model_ema = m * model_ema + (1 - m) model (util.py:124-127), as two multi-tensor ops
+    instead of 2 x #params tiny launches."""
+    p_ema = [p.data for p in model_ema.parameters()]
+    p = [p.detach().data for p in model.parameters()]
+    torch._foreach_mul_(p_ema, m)
+    torch._foreach_add_(p_ema, p, alpha=1 - m)
