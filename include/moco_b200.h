@@ -87,6 +87,13 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype,
                  float* loss_prob, float* dq_or_null,
                  void* workspace, size_t workspace_bytes, int flags, void* stream);
 
+/* Profiling hook (bench.py's roofline): while set, moco_nce_fwd records the CUDA
+ * events `ev_start` / `ev_stop` (cudaEvent_t) on its stream immediately before /
+ * after launching kernel `kernel` (MOCO_PROF_STATS: the q.Queue^T statistics
+ * kernel; MOCO_PROF_DQ: the dq kernel).  Pass NULLs to clear.  Not thread-safe. */
+enum { MOCO_PROF_STATS = 1, MOCO_PROF_DQ = 2 };
+int moco_prof_set_events(int kernel, void* ev_start, void* ev_stop);
+
 /* Backward of the dense-logits compatibility API (MemoryMoCo.forward returning
  * `out`, then an arbitrary upstream gradient):
  *   dq_i = inv_T * ( g_i0 * k_i + sum_j g_i,1+j * queue_j ),  g = grad_logits [N, K+1] fp32.

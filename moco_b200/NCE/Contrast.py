@@ -149,7 +149,7 @@ class MemoryMoCo(nn.Module):
         self.register_buffer('memory_bf16', torch.empty(0, dtype=torch.bfloat16), persistent=False)
         self._bf16_src = None      # (data_ptr, _version) of `memory` the bf16 copy was built from
         self._scratch = {}
-        self._register_load_state_dict_post_hook(lambda m, keys: m._invalidate())
+        self.register_load_state_dict_post_hook(lambda m, keys: m._invalidate())
 
     # -- bf16 working queue -------------------------------------------------
     def _invalidate(self):

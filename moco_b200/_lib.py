@@ -25,6 +25,7 @@ SIGNATURES = {
     "moco_nce_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_size_t, c_int, c_void_p]),
+    "moco_prof_set_events": (c_int, [c_int, c_void_p, c_void_p]),
     "moco_nce_bwd_dense": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
                                    c_void_p, c_void_p]),
     "moco_queue_enqueue": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_void_p]),
@@ -65,8 +66,52 @@ def load() -> ctypes.CDLL:
         fn.argtypes = args
     if lib.moco_abi_version() != 1:
         raise RuntimeError("moco_b200: ABI version mismatch between _lib.py and libmoco_b200.so")
-    _lib = lib
-    return lib
+    _lib = _Counting(lib)
+    return _lib
+
+
+# kernels launched per successful C-ABI call (bench.py reports the total as `gpu_launches`)
+launches = 0
+
+
+class _Counting:
+    """Thin proxy over the CDLL that counts this library's kernel launches."""
+
+    _PER_CALL = {"moco_queue_enqueue": 1, "moco_f32_to_bf16": 1, "moco_shuffle_gather": 1,
+                 "moco_signal_barrier": 1, "moco_nce_bwd_dense": 1}
+
+    def __init__(self, lib):
+        self._lib = lib
+        for name in SIGNATURES:
+            fn = getattr(lib, name)
+            if name == "moco_nce_fwd":
+                setattr(self, name, self._wrap_nce(fn))
+            elif name in self._PER_CALL:
+                setattr(self, name, self._wrap(fn, self._PER_CALL[name]))
+            else:
+                setattr(self, name, fn)
+
+    @staticmethod
+    def _wrap(fn, n):
+        def call(*a):
+            global launches
+            rc = fn(*a)
+            if rc == 0:
+                launches += n
+            return rc
+        return call
+
+    @staticmethod
+    def _wrap_nce(fn):
+        def call(*a):
+            global launches
+            rc = fn(*a)
+            if rc == 0:
+                simt = bool(a[16] & NCE_FORCE_SIMT) or a[5] % 64 != 0 or a[5] > 256
+                # prep + (stats + combine [+ dq + dq_reduce]) on the tcgen05 path, prep + row kernel otherwise
+                launches += 2 if simt else (5 if a[13] else 3)
+            return rc
+        return call
 
 
 def check(code: int, what: str) -> None:

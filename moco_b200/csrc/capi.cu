@@ -43,6 +43,12 @@ static DevInfo device_info() {
     return d;
 }
 
+// optional profiling hook: CUDA events recorded right before / after one kernel of moco_nce_fwd
+static cudaEvent_t g_prof_ev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+static inline void prof_mark(int kernel, int which, cudaStream_t s) {
+    if (g_prof_ev[kernel][which]) cudaEventRecord(g_prof_ev[kernel][which], s);
+}
+
 }  // namespace moco
 
 using namespace moco;
@@ -111,13 +117,17 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
         p.cta_group = (flags & MOCO_NCE_CTA_PAIR) ? 2 : 1;
         p.num_sms = d.sms;
         p.slices = 0; p.n_pad = 0;
+        prof_mark(MOCO_PROF_STATS, 0, stream);
         e = launch_nce_tc(p, ws, stream);
+        prof_mark(MOCO_PROF_STATS, 1, stream);
         if (e == cudaSuccess) {
             e = launch_combine(N, C, p.slices, p.n_pad, inv_T, logits, K, lse, loss_rows, prob_rows, loss_prob, ws, stream);
             if (e != cudaSuccess) return cuda_fail("combine kernel", e);
             if (dq) {
                 int slices = 0, n_pad = 0;
+                prof_mark(MOCO_PROF_DQ, 0, stream);
                 e = launch_nce_dq_tc(qb, queue, N, C, K, inv_T, lse, d.sms, &slices, &n_pad, ws, stream);
+                prof_mark(MOCO_PROF_DQ, 1, stream);
                 if (e != cudaSuccess) return cuda_fail("tcgen05 dq kernel", e);
                 e = launch_dq_reduce(N, C, slices, n_pad, inv_T, k, qk_dtype, prob_rows, dq, ws, stream);
                 if (e != cudaSuccess) return cuda_fail("dq reduce kernel", e);
@@ -130,6 +140,14 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
     }
     e = launch_simt_rows(qb, k, qk_dtype, queue, N, C, K, inv_T, logits, lse, loss_rows, prob_rows, loss_prob, dq, ws, stream);
     if (e != cudaSuccess) return cuda_fail("generic NCE kernel", e);
+    return MOCO_OK;
+}
+
+int moco_prof_set_events(int kernel, void* ev_start, void* ev_stop) {
+    g_err[0] = 0;
+    if (kernel < 0 || kernel > 2) { set_error("moco_prof_set_events: bad kernel id"); return MOCO_ERR_INVALID; }
+    g_prof_ev[kernel][0] = static_cast<cudaEvent_t>(ev_start);
+    g_prof_ev[kernel][1] = static_cast<cudaEvent_t>(ev_stop);
     return MOCO_OK;
 }
 

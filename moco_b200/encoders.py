@@ -1,0 +1,96 @@
+"""Query / key encoders for the MoCo step (host PyTorch, as BASELINE.json:north_star keeps them).
+
+Plain ResNet-18/34/50 with the MoCo head of the reference's variant
+(``moco/models/resnet.py:109,125-126,177-178``: ``fc`` to ``low_dim`` followed by
+L2 normalisation).  Out of the hot-path scope -- these exist to
+drive the end-to-end step / benchmark; all conv/BN math is cuDNN via PyTorch.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+
+class _Basic(nn.Module):
+    expansion = 1
+
+    def __init__(self, cin, planes, stride):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, planes, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.short = None
+        if stride != 1 or cin != planes:
+            self.short = nn.Sequential(nn.Conv2d(cin, planes, 1, stride, bias=False), nn.BatchNorm2d(planes))
+
+    def forward(self, x):
+        y = F.relu(self.bn1(self.conv1(x)), inplace=True)
+        y = self.bn2(self.conv2(y))
+        return F.relu(y + (x if self.short is None else self.short(x)), inplace=True)
+
+
+class _Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, cin, planes, stride):
+        super().__init__()
+        cout = planes * 4
+        self.conv1 = nn.Conv2d(cin, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, cout, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(cout)
+        self.short = None
+        if stride != 1 or cin != cout:
+            self.short = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+
+    def forward(self, x):
+        y = F.relu(self.bn1(self.conv1(x)), inplace=True)
+        y = F.relu(self.bn2(self.conv2(y)), inplace=True)
+        y = self.bn3(self.conv3(y))
+        return F.relu(y + (x if self.short is None else self.short(x)), inplace=True)
+
+
+class MoCoResNet(nn.Module):
+    """ResNet trunk -> global average pool -> fc(low_dim) -> L2 normalise."""
+
+    def __init__(self, block, depths, low_dim=128, width=1):
+        super().__init__()
+        base = int(64 * width)
+        self.stem = nn.Sequential(nn.Conv2d(3, 64, 7, 2, 3, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True),
+                                  nn.MaxPool2d(3, 2, 1))
+        layers, cin = [], 64
+        for i, d in enumerate(depths):
+            planes = base * (2 ** i)
+            for j in range(d):
+                layers.append(block(cin, planes, (1 if i == 0 else 2) if j == 0 else 1))
+                cin = planes * block.expansion
+        self.layers = nn.Sequential(*layers)
+        self.fc = nn.Linear(cin, low_dim)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    def forward(self, x):
+        x = self.layers(self.stem(x))
+        x = torch.flatten(F.adaptive_avg_pool2d(x, 1), 1)
+        x = self.fc(x).float()
+        return x / x.pow(2).sum(1, keepdim=True).sqrt()       # Normalize(power=2), resnet.py:30-33
+
+
+def resnet18(low_dim=128, width=1):
+    return MoCoResNet(_Basic, [2, 2, 2, 2], low_dim, width)
+
+
+def resnet34(low_dim=128, width=1):
+    return MoCoResNet(_Basic, [3, 4, 6, 3], low_dim, width)
+
+
+def resnet50(low_dim=128, width=1):
+    return MoCoResNet(_Bottleneck, [3, 4, 6, 3], low_dim, width)

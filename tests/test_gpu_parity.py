@@ -1,0 +1,276 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200): the CUDA path, called through the C ABI
+(ctypes -> libmoco_b200.so) by the Python mirror of the reference API, against
+(a) the golden vectors produced by the unmodified reference and (b) the numpy oracle on seeded
+inputs.  Tolerances: logits 1e-3 relative to max|logit| (BASELINE.json north_star) on identical
+bf16-representable inputs -- in practice ~1e-6; queue contents / indices / shuffles bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import moco_oracle as O
+from tests.helpers import oracle_head_chunked, rand_unit
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_RTOL = 1e-3          # north_star tolerance
+TIGHT = 2e-5               # what identical bf16 inputs + fp32 accumulation actually give
+
+
+def _flags():
+    from moco_b200 import _lib
+    return {"auto": _lib.NCE_AUTO, "simt": _lib.NCE_FORCE_SIMT, "tc1": _lib.NCE_SINGLE_CTA, "tc2": _lib.NCE_CTA_PAIR}
+
+
+@pytest.fixture(scope="module")
+def contrast_golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "contrast.npz"))
+
+
+def test_library_is_the_cuda_one():
+    from moco_b200 import _lib
+    lib = _lib.load()
+    import ctypes
+    sm, major = ctypes.c_int(), ctypes.c_int()
+    assert lib.moco_device_info(ctypes.byref(sm), ctypes.byref(major), None) == 0
+    assert major.value == 10 and sm.value >= 100, "expected a Blackwell (sm_100) device"
+
+
+@pytest.mark.parametrize("flag", ["auto", "simt", "tc1", "tc2"])
+@pytest.mark.parametrize("name", ["c1head", "wrap", "c256", "ragged"])
+def test_golden_dense_api(contrast_golden, name, flag):
+    """Unchanged reference call-site (train.py:262-264,273): contrast(q,k,k_all) -> criterion(out)
+    -> backward, step after step, vs. the reference's own outputs."""
+    from moco_b200.NCE import MemoryMoCo, NCESoftmaxLoss, fused_prob
+    g = contrast_golden
+    N, C, K, A, steps = (int(v) for v in g[f"{name}_meta"])
+    T = float(g[f"{name}_T"][0])
+    mod = MemoryMoCo(C, K, T)
+    assert sorted(mod.state_dict().keys()) == ["memory", "params"]
+    mod.memory.copy_(torch.from_numpy(g[f"{name}_memory0"]))
+    mod = mod.cuda()
+    mod.kernel_flags = _flags()[flag]
+    crit = NCESoftmaxLoss().cuda()
+    for s in range(steps):
+        q = torch.from_numpy(g[f"{name}_s{s}_q"]).cuda().requires_grad_(True)
+        k = torch.from_numpy(g[f"{name}_s{s}_k"]).cuda()
+        k_all = torch.from_numpy(g[f"{name}_s{s}_k_all"]).cuda()
+        assert mod.index == int(g[f"{name}_s{s}_index"][0])
+        out = mod(q, k, k_all)
+        ref = g[f"{name}_s{s}_logits"]
+        assert out.shape == (N, K + 1) and out.dtype == torch.float32 and out.is_contiguous()
+        err = np.abs(out.detach().cpu().numpy() - ref).max() / np.abs(ref).max()
+        assert err < TIGHT < LOGIT_RTOL, err
+        loss = crit(out)
+        assert abs(float(loss) - float(g[f"{name}_s{s}_loss"][0])) < 1e-4
+        assert abs(float(fused_prob(out)) - float(g[f"{name}_s{s}_prob"][0])) < 1e-5
+        # the generic definitions on the dense logits agree with the fused scalars
+        assert abs(float(torch.softmax(out, 1)[:, 0].mean()) - float(g[f"{name}_s{s}_prob"][0])) < 1e-5
+        loss.backward()
+        dq_ref = g[f"{name}_s{s}_dq"]
+        dq_err = np.abs(q.grad.cpu().numpy() - dq_ref).max() / np.abs(dq_ref).max()
+        assert dq_err < 5e-3, dq_err          # P is rounded to bf16 before the P.Queue MMA
+        assert mod.index == int(g[f"{name}_s{s}_index"][1])
+    # FIFO contents bit-exact (Contrast.py:32-34), including the mid-batch wrap of "wrap"
+    np.testing.assert_array_equal(mod.memory.cpu().numpy(), g[f"{name}_memory_final"])
+    np.testing.assert_array_equal(mod.memory_bf16.float().cpu().numpy(), g[f"{name}_memory_final"])
+
+
+@pytest.mark.parametrize("name", ["c1head", "c256"])
+def test_golden_dense_backward_through_logits(contrast_golden, name):
+    """Autograd through the dense `out` itself (arbitrary upstream gradient), not via the fused loss."""
+    from moco_b200.NCE import MemoryMoCo
+    g = contrast_golden
+    N, C, K, A, steps = (int(v) for v in g[f"{name}_meta"])
+    T = float(g[f"{name}_T"][0])
+    mod = MemoryMoCo(C, K, T)
+    mod.memory.copy_(torch.from_numpy(g[f"{name}_memory0"]))
+    mod = mod.cuda()
+    q = torch.from_numpy(g[f"{name}_s0_q"]).cuda().requires_grad_(True)
+    k = torch.from_numpy(g[f"{name}_s0_k"]).cuda()
+    out = mod(q, k, torch.from_numpy(g[f"{name}_s0_k_all"]).cuda())
+    out = out * 1.0                                   # drops the fused attachment
+    loss = torch.nn.functional.cross_entropy(out, torch.zeros(N, dtype=torch.long, device="cuda"))
+    loss.backward()
+    dq_ref = g[f"{name}_s0_dq"]
+    assert np.abs(q.grad.cpu().numpy() - dq_ref).max() / np.abs(dq_ref).max() < 1e-4
+
+
+CASES = {
+    # BASELINE.json configs (head shapes): name -> (N, C, K, T)
+    "c1": (32, 128, 1024, 0.07),
+    "c2": (256, 128, 16384, 0.07),
+    "c3": (256, 128, 65536, 0.07),
+    "c4_shard": (2048, 128, 16384, 0.07),     # all 2048 queries x one 16384-row shard
+    "c5": (512, 256, 262144, 0.07),
+    "ragged": (130, 192, 1000, 0.2),
+    "k126689": (128, 128, 126689, 0.1),       # scripts/...sh:12 queue length (not a multiple of anything)
+    "tiny": (1, 64, 1, 0.07),
+}
+
+
+@pytest.mark.parametrize("flag", ["tc1", "tc2"])
+@pytest.mark.parametrize("case", list(CASES))
+def test_fused_vs_oracle(case, flag):
+    from moco_b200.NCE import MemoryMoCo
+    N, C, K, T = CASES[case]
+    rng = np.random.default_rng(hash(case) % 2**31 if False else sum(map(ord, case)))
+    q, k = rand_unit(rng, N, C), rand_unit(rng, N, C)
+    memory = O.bf16_round((rng.random((K, C), dtype=np.float32) * 2 - 1) * O.queue_init_bound(C)) \
+        if case in ("c1", "tiny") else rand_unit(rng, K, C)
+    lse, loss, prob, dq = oracle_head_chunked(q, k, memory, T)
+    mod = MemoryMoCo(C, K, T)
+    mod.memory.copy_(torch.from_numpy(memory))
+    mod = mod.cuda()
+    mod.kernel_flags = _flags()[flag]
+    qt = torch.from_numpy(q).cuda().requires_grad_(True)
+    kt = torch.from_numpy(k).cuda()
+    k_all = kt[: min(N, K)]
+    l, p = mod.forward_loss(qt, kt, k_all)
+    assert abs(float(l) - loss) < 2e-4 * max(1.0, abs(loss)), (float(l), loss)
+    assert abs(float(p) - prob) < 1e-3 * prob + 1e-9
+    lse_gpu = mod._scratch[(N, C, K, qt.device)].lse.cpu().numpy()
+    assert np.abs(lse_gpu - lse).max() < 2e-4
+    l.backward()
+    err = np.abs(qt.grad.cpu().numpy() - dq).max() / np.abs(dq).max()
+    assert err < 5e-3, err
+    # enqueue happened after the logits were taken (S2) and in order (S3/S4)
+    assert mod.index == min(N, K) % K
+    exp = memory.copy()
+    exp[O.enqueue_ids(0, min(N, K), K)] = k[: min(N, K)]
+    np.testing.assert_array_equal(mod.memory.cpu().numpy(), exp)
+
+
+def test_fp32_inputs_within_north_star_tolerance():
+    """Arbitrary fp32 (not bf16-representable) q/k/queue: logits within 1e-3 relative of the fp32 oracle."""
+    from moco_b200.NCE import MemoryMoCo
+    rng = np.random.default_rng(5)
+    N, C, K, T = 64, 128, 4096, 0.07
+    q = O.l2_normalize(rng.standard_normal((N, C)).astype(np.float32))
+    k = O.l2_normalize(rng.standard_normal((N, C)).astype(np.float32))
+    memory = O.l2_normalize(rng.standard_normal((K, C)).astype(np.float32))
+    ref = O.MemoryMoCoOracle(memory, T).logits(q, k)
+    mod = MemoryMoCo(C, K, T)
+    mod.memory.copy_(torch.from_numpy(memory))
+    mod = mod.cuda()
+    out = mod(torch.from_numpy(q).cuda(), torch.from_numpy(k).cuda(), torch.from_numpy(k).cuda())
+    err = np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert err < LOGIT_RTOL, err
+    # the positive logit is computed in fp32 from the fp32 inputs: tight
+    assert np.abs(out[:, 0].cpu().numpy() - ref[:, 0]).max() < 1e-4
+    # the fp32 master queue keeps the exact fp32 keys, the working copy their bf16 rounding
+    np.testing.assert_array_equal(mod.memory[:N].cpu().numpy(), k)
+    np.testing.assert_array_equal(mod.memory_bf16[:N].float().cpu().numpy(), O.bf16_round(k))
+
+
+def test_bf16_inputs_accepted():
+    from moco_b200.NCE import MemoryMoCo
+    rng = np.random.default_rng(6)
+    N, C, K, T = 128, 128, 2048, 0.07
+    q, k, memory = rand_unit(rng, N, C), rand_unit(rng, N, C), rand_unit(rng, K, C)
+    _, loss, prob, _ = oracle_head_chunked(q, k, memory, T, want_dq=False)
+    mod = MemoryMoCo(C, K, T)
+    mod.memory.copy_(torch.from_numpy(memory))
+    mod = mod.cuda()
+    l, p = mod.forward_loss(torch.from_numpy(q).cuda().bfloat16(), torch.from_numpy(k).cuda().bfloat16(),
+                            torch.from_numpy(k).cuda().bfloat16())
+    assert abs(float(l) - loss) < 2e-4 and abs(float(p) - prob) < 1e-3 * prob
+
+
+def test_deterministic_and_no_state_leak():
+    from moco_b200.NCE import MemoryMoCo
+    rng = np.random.default_rng(7)
+    N, C, K, T = 256, 128, 16384, 0.07
+    q, k, memory = rand_unit(rng, N, C), rand_unit(rng, N, C), rand_unit(rng, K, C)
+    outs = []
+    for _ in range(3):
+        mod = MemoryMoCo(C, K, T)
+        mod.memory.copy_(torch.from_numpy(memory))
+        mod = mod.cuda()
+        qt = torch.from_numpy(q).cuda().requires_grad_(True)
+        l, p = mod.forward_loss(qt, torch.from_numpy(k).cuda(), torch.from_numpy(k).cuda())
+        l.backward()
+        outs.append((float(l), float(p), qt.grad.cpu().numpy().copy()))
+    for o in outs[1:]:
+        assert o[0] == outs[0][0] and o[1] == outs[0][1]
+        np.testing.assert_array_equal(o[2], outs[0][2])
+
+
+@pytest.mark.parametrize("K,C,n_all,index", [(40, 64, 16, 32), (126689, 128, 1024, 126000), (65536, 128, 2048, 0),
+                                             (1000, 100, 10, 995), (8, 64, 8, 3)])
+def test_enqueue_ring_bit_exact(K, C, n_all, index):
+    from moco_b200.NCE import MemoryMoCo
+    rng = np.random.default_rng(K + n_all)
+    memory = rng.standard_normal((K, C)).astype(np.float32)
+    orc = O.MemoryMoCoOracle(memory, 0.07, index=index)
+    mod = MemoryMoCo(C, K, 0.07)
+    mod.memory.copy_(torch.from_numpy(memory))
+    mod = mod.cuda()
+    mod.index = index
+    for step in range(3):
+        k_all = rng.standard_normal((n_all, C)).astype(np.float32)
+        ids = orc.enqueue(k_all)
+        np.testing.assert_array_equal(ids, (np.arange(n_all) + (index + step * n_all) % K) % K)
+        mod.enqueue(torch.from_numpy(k_all).cuda())
+        assert mod.index == orc.index
+    np.testing.assert_array_equal(mod.memory.cpu().numpy(), orc.memory)
+    np.testing.assert_array_equal(mod._queue_bf16().float().cpu().numpy(), O.bf16_round(orc.memory))
+
+
+def test_enqueue_rejects_oversized_batch():
+    from moco_b200.NCE import MemoryMoCo
+    mod = MemoryMoCo(64, 8, 0.07).cuda()
+    with pytest.raises(RuntimeError, match="n_all"):
+        mod.enqueue(torch.zeros(9, 64, device="cuda"))
+
+
+def test_state_dict_roundtrip_reference_format():
+    from moco_b200.NCE import MemoryMoCo
+    a = MemoryMoCo(128, 256, 0.07).cuda()
+    a.enqueue(torch.nn.functional.normalize(torch.randn(32, 128, device="cuda"), dim=1))
+    sd = {k: v.cpu() for k, v in a.state_dict().items()}
+    assert sorted(sd) == ["memory", "params"] and sd["memory"].dtype == torch.float32
+    assert sd["params"].tolist() == [-1]
+    b = MemoryMoCo(128, 256, 0.07).cuda()
+    b.load_state_dict(sd)
+    assert b.index == 0                                  # the reference does not checkpoint `index`
+    np.testing.assert_array_equal(b.memory.cpu().numpy(), sd["memory"].numpy())
+    np.testing.assert_array_equal(b._queue_bf16().float().cpu().numpy(), O.bf16_round(sd["memory"].numpy()))
+
+
+def test_shufflebn_single_rank_roundtrip(golden_dir):
+    """W = 1: the reference still permutes within the batch."""
+    from moco_b200.util import DistributedShufle
+    g = np.load(os.path.join(golden_dir, "shuffle.npz"))
+    x = torch.from_numpy(g["w1_n8_e3_r0_x"]).cuda()
+    xs, binds = DistributedShufle.forward_shuffle(x, 3)
+    np.testing.assert_array_equal(xs.cpu().numpy(), g["w1_n8_e3_r0_x_shuf"])
+    np.testing.assert_array_equal(binds.cpu().numpy(), g["w1_n8_e3_r0_binds"])
+    assert binds.dtype == torch.int64 and binds.is_cuda
+    feat = torch.from_numpy(g["w1_n8_e3_r0_feat"]).cuda()
+    f_all, f_loc = DistributedShufle.backward_shuffle(feat, binds, return_local=True)
+    np.testing.assert_array_equal(f_all.cpu().numpy(), g["w1_n8_e3_r0_feat_all"])
+    np.testing.assert_array_equal(f_loc.cpu().numpy(), g["w1_n8_e3_r0_feat_local"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_shufflebn_full_size_images_roundtrip(dtype):
+    """BASELINE batch (256 x 3 x 224 x 224) through the bulk-async gather; properties: it is the oracle's
+    permutation, and backward(forward(x)) == x."""
+    from moco_b200.util import DistributedShufle
+    n, epoch = 256, 11
+    x = torch.randn(n, 3, 224, 224, device="cuda").to(dtype)
+    xs, binds = DistributedShufle.forward_shuffle(x, epoch)
+    fwd, bwd = O.get_shuffle_ids(n, epoch)
+    np.testing.assert_array_equal(binds.cpu().numpy(), bwd)
+    assert torch.equal(xs, x[torch.from_numpy(fwd).cuda()])
+    back = DistributedShufle.backward_shuffle(xs, binds, return_local=False)
+    assert torch.equal(back, x)
+
+
+def test_cpu_tensors_fail_loudly():
+    from moco_b200.NCE import MemoryMoCo
+    mod = MemoryMoCo(64, 32, 0.07)          # never moved to CUDA
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mod(torch.randn(4, 64), torch.randn(4, 64), torch.randn(4, 64))
