@@ -1,0 +1,123 @@
+"""Multi-GPU ShuffleBN check + NVLink gather bandwidth (run under torch.distributed.run, one rank per GPU).
+
+Each rank regenerates EVERY rank's batch from per-rank seeds, so it can evaluate the numpy oracle of the
+reference's all_gather + index ShuffleBN locally and compare its own P2P-pulled result bit for bit.
+Prints one JSON line from rank 0.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from moco_b200 import _lib  # noqa: E402
+from moco_b200.util import DistributedShufle, ShuffleContext, dist_collect  # noqa: E402
+from oracle import moco_oracle as O  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    res = {"world": world, "ok": True}
+
+    def batch(r, n, shape, seed):
+        g = torch.Generator().manual_seed(seed * 1000 + r)
+        return torch.randn(n, *shape, generator=g)
+
+    # ---- correctness: small images + features, several epochs, both directions, repeated (double buffering)
+    for it, (n, epoch) in enumerate([(8, 1), (8, 2), (16, 7), (8, 1)]):
+        xs = [batch(r, n, (3, 8, 8), 10 + it) for r in range(world)]
+        outs, bwd = O.forward_shuffle([x.numpy() for x in xs], epoch)
+        mine, binds = DistributedShufle.forward_shuffle(xs[rank].to(dev), epoch)
+        ok = np.array_equal(mine.cpu().numpy(), outs[rank]) and np.array_equal(binds.cpu().numpy(), bwd)
+        feats = [torch.from_numpy(o.reshape(n, -1)[:, :32].copy()) for o in outs]          # stand-in key encoder
+        f_all, f_loc = O.backward_shuffle([f.numpy() for f in feats], bwd, True)
+        g_all, g_loc = DistributedShufle.backward_shuffle(feats[rank].to(dev), binds, True)
+        ok = ok and np.array_equal(g_all.cpu().numpy(), f_all) and np.array_equal(g_loc.cpu().numpy(), f_loc[rank])
+        # S6: un-shuffled local features line up with this rank's own images
+        ok = ok and np.array_equal(g_loc.cpu().numpy(), xs[rank].numpy().reshape(n, -1)[:, :32])
+        res[f"iter{it}"] = bool(ok)
+        res["ok"] = res["ok"] and bool(ok)
+    col = dist_collect(xs[rank].to(dev))
+    ok = np.array_equal(col.cpu().numpy(), O.dist_collect([x.numpy() for x in xs]))
+    res["dist_collect"] = bool(ok)
+    res["ok"] = res["ok"] and bool(ok)
+
+    # ---- bandwidth: BASELINE batch (256 x 3 x 224 x 224), fp32 and bf16, bulk-async vs LDG kernels
+    ctx = ShuffleContext.get()
+    n = 256
+    for dt, tag in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+        x = torch.randn(n, 3, 224, 224, device=dev).to(dt)
+        for flags, kname in ((_lib.GATHER_AUTO, "bulk"), (_lib.GATHER_LDG, "ldg")):
+            ctx.gather_flags = flags
+            for _ in range(3):
+                DistributedShufle.forward_shuffle(x, 5)
+            torch.cuda.synchronize()
+            dist.barrier()
+            iters = 10
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                y, _ = DistributedShufle.forward_shuffle(x, 5)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            row_bytes = 3 * 224 * 224 * x.element_size()
+            fwd, _ = O.get_shuffle_ids(n * world, 5)
+            remote = int(((fwd[rank * n:(rank + 1) * n] // n) != rank).sum())
+            res[f"fwd_shuffle_{tag}_{kname}_us"] = float(ms) * 1e3          # staging copy + barrier + gather
+            res[f"fwd_shuffle_{tag}_{kname}_pull_GBps"] = n * row_bytes / (float(ms) * 1e-3) / 1e9
+            res[f"remote_rows_{tag}"] = remote
+            fwd_t = torch.from_numpy(fwd).to(dev)
+            gathered = [torch.empty_like(x) for _ in range(world)]          # expected rows via NCCL, for the check
+            dist.all_gather(gathered, x)
+            exp = torch.cat(gathered)[fwd_t[rank * n:(rank + 1) * n]]
+            okb = bool(torch.equal(y, exp))
+            res[f"fwd_shuffle_{tag}_{kname}_ok"] = okb
+            res["ok"] = res["ok"] and okb
+        ctx.gather_flags = _lib.GATHER_AUTO
+    # gather kernel alone (no staging copy / barrier): time the C call on pre-staged data
+    x = torch.randn(n, 3, 224, 224, device=dev).bfloat16()
+    buf = ctx._staging("fwd", x.numel() * 2)
+    buf.tensor(x.shape, x.dtype).copy_(x)
+    ctx.barrier()
+    fwd, _ = O.get_shuffle_ids(n * world, 9)
+    src = torch.from_numpy(fwd[rank * n:(rank + 1) * n].copy()).to(dev)
+    out = torch.empty_like(x)
+    lib = _lib.load()
+    for flags, kname in ((0, "bulk"), (1, "ldg")):
+        def call():
+            return lib.moco_shuffle_gather(buf.table, world, n, src.data_ptr(), n, 3 * 224 * 224 * 2,
+                                           out.data_ptr(), flags, torch.cuda.current_stream().cuda_stream)
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            call()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / 20], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        remote = int(((fwd[rank * n:(rank + 1) * n] // n) != rank).sum())
+        res[f"gather_only_bf16_{kname}_us"] = float(ms) * 1e3
+        res[f"gather_only_bf16_{kname}_nvlink_GBps"] = remote * 3 * 224 * 224 * 2 / (float(ms) * 1e-3) / 1e9
+    ctx.barrier()
+    dist.barrier()
+    if rank == 0:
+        print(json.dumps(res))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
