@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--feat-dim", type=int, default=128)
     ap.add_argument("--nce-k", type=int, default=0, help="queue length (0: 16384 at 1 GPU, 65536 otherwise)")
     ap.add_argument("--nce-t", type=float, default=0.07)
+    ap.add_argument("--memory-format", default="channels_last", choices=["channels_last", "contiguous"],
+                    help="encoder activation layout (host PyTorch side)")
     ap.add_argument("--no-stress", action="store_true", help="skip the c5 roofline-stress microbench")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
@@ -195,8 +197,9 @@ def run_native(args):
     K = args.nce_k or (16384 if world == 1 else 65536)
     torch.manual_seed(0)
     ctor = getattr(encoders, args.arch)
-    model = ctor(low_dim=C).to(dev).to(memory_format=torch.channels_last)
-    model_ema = ctor(low_dim=C).to(dev).to(memory_format=torch.channels_last)
+    mf = torch.channels_last if args.memory_format == "channels_last" else torch.contiguous_format
+    model = ctor(low_dim=C).to(dev).to(memory_format=mf)
+    model_ema = ctor(low_dim=C).to(dev).to(memory_format=mf)
     model_ema.load_state_dict(model.state_dict())
     contrast = MemoryMoCo(C, K, T).to(dev)
     opt = torch.optim.SGD(model.parameters(), lr=0.03 * N * world / 256, momentum=0.9, weight_decay=1e-4)
@@ -211,7 +214,7 @@ def run_native(args):
 
     def split(t):
         x1, x2 = torch.split(t, [3, 3], dim=1)
-        return (x1.contiguous(memory_format=torch.channels_last), x2.contiguous())
+        return (x1.contiguous(memory_format=mf), x2.contiguous())
 
     def barrier():
         if world > 1:

@@ -116,6 +116,8 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
         p.q_bf16 = qb; p.queue = queue; p.N = N; p.C = C; p.K = K; p.inv_T = inv_T; p.logits = logits;
         p.cta_group = (flags & MOCO_NCE_CTA_PAIR) ? 2 : 1;
         p.num_sms = d.sms;
+        const int max_share = (flags & MOCO_NCE_SHARE4) ? 4 : ((flags & MOCO_NCE_SHARE2) ? 2 : 1);
+        p.max_share = max_share;
         p.slices = 0; p.n_pad = 0;
         prof_mark(MOCO_PROF_STATS, 0, stream);
         e = launch_nce_tc(p, ws, stream);
@@ -126,7 +128,10 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
             if (dq) {
                 int slices = 0, n_pad = 0;
                 prof_mark(MOCO_PROF_DQ, 0, stream);
-                e = launch_nce_dq_tc(qb, queue, N, C, K, inv_T, lse, d.sms, &slices, &n_pad, ws, stream);
+                if (flags & MOCO_NCE_DQ_V2)
+                    e = launch_nce_dq2_tc(qb, queue, N, C, K, inv_T, lse, d.sms, max_share, &slices, &n_pad, ws, stream);
+                else
+                    e = launch_nce_dq_tc(qb, queue, N, C, K, inv_T, lse, d.sms, max_share, &slices, &n_pad, ws, stream);
                 prof_mark(MOCO_PROF_DQ, 1, stream);
                 if (e != cudaSuccess) return cuda_fail("tcgen05 dq kernel", e);
                 e = launch_dq_reduce(N, C, slices, n_pad, inv_T, k, qk_dtype, prob_rows, dq, ws, stream);

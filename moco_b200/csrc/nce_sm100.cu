@@ -16,21 +16,21 @@
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "tc_common.cuh"
 
 namespace moco {
-
-constexpr int kSlab = 128 * 128;            // bytes of a [128 rows x 64 bf16] swizzled slab
-constexpr int kSmemBudget = 232448 - 1024;  // max dynamic smem per CTA minus alignment slack
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // =====================================================================================
 // Kernel A: per-slice softmax statistics (and optional dense logits)
 // =====================================================================================
 constexpr int kStatsBN = 256;          // queue rows per tile (UMMA N)
-constexpr int kStatsThreads = 384;     // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
+// Epilogue warps: 2 per SM sub-partition.  Measured on B200 (tools/pipe_probe.py): the accumulator drain
+// (tcgen05.ld, ~64 B/clk/SM) is the floor of the epilogue, not MUFU/issue latency -- 16 warps were slower
+// (68.9 us vs 63.8 us at N=512, C=256, K=262144) than 8.
+constexpr int kEpiWarps = 8;
+constexpr int kEpiCols = kStatsBN / (kEpiWarps / 4);   // accumulator columns per epilogue thread per tile
+constexpr int kEpiChunks = kEpiCols / 32;              // 32-column tcgen05.ld per thread per tile
+constexpr int kStatsThreads = 128 + kEpiWarps * 32;    // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4.. epilogue
 
 struct StatsArgs {
     int N, C, K;
@@ -38,9 +38,13 @@ struct StatsArgs {
     float inv_T;
     float* logits;        // optional [N, K+1]
     float2* part_ms;      // [slices, n_pad]
+    int debug;            // bring-up only (env MOCO_DEBUG_MODE): 1 = no epilogue math, 2 = no MMA issue, 4 = no TMA
 };
 
-template <int G>
+// G  = tcgen05 cta_group (1: M = 128 per CTA; 2: M = 256 per CTA pair, B tile split across the pair)
+// CS = CTAs per cluster that handle DIFFERENT q row blocks but the SAME queue tiles (G == 1 only): each
+//      loads 1/CS of every queue tile and TMA-multicasts it to all CS CTAs, dividing L2->SM traffic by CS.
+template <int G, int CS>
 __global__ void __launch_bounds__(kStatsThreads, 1)
 nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_queue,
                  const StatsArgs a) {
@@ -58,13 +62,19 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     uint64_t* tempty = bars + 2 * NS + 2;
     uint64_t* qfull = bars + 2 * NS + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 5);
-    float2* red_s = reinterpret_cast<float2*>(bars + 2 * NS + 6);   // [128]
+    float2* red_s = reinterpret_cast<float2*>(bars + 2 * NS + 6);   // [kEpiWarps/4 - 1][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = (G == 2) ? cluster_ctarank() : 0u;
-    const int cluster_id = blockIdx.x / G;
-    const int mblk = cluster_id % a.mblks;
-    const int slice = cluster_id / a.mblks;
+    static_assert(G == 1 || CS == 1, "multicast sharing is implemented for cta_group::1 only");
+    constexpr int kCluster = G * CS;
+    constexpr bool kClustered = kCluster > 1;
+    constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
+    const uint32_t crank = kClustered ? cluster_ctarank() : 0u;
+    const uint32_t rank = (G == 2) ? crank : 0u;               // rank inside the MMA pair
+    const int cluster_id = blockIdx.x / kCluster;
+    const int mgroups = a.mblks / CS;                           // host guarantees CS | mblks
+    const int mblk = (cluster_id % mgroups) * CS + ((CS > 1) ? (int)crank : 0);
+    const int slice = cluster_id / mgroups;
     const int t0 = (int)(((long long)slice * a.num_tiles) / a.slices);
     const int t1 = (int)(((long long)(slice + 1) * a.num_tiles) / a.slices);
     const int row0 = (mblk * G + (int)rank) * kRowsPerCta;
@@ -74,8 +84,8 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tma_prefetch_desc(&tm_queue);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8 * G); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CS); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kEpiWarps * G); }
         mbar_init(qfull, 1);
         fence_mbar_init();
     }
@@ -84,7 +94,7 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tmem_relinquish<G>();
     }
     tc_fence_before();
-    if (G == 2) cluster_sync_all(); else __syncthreads();
+    if (kClustered) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -104,9 +114,18 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     const int st = it % NS;
                     const uint32_t ph = (uint32_t)(it / NS) & 1u;
                     mbar_wait(&empty[st], ph ^ 1u);
+                    if (a.debug & 4) { if (rank == 0) mbar_arrive(&full[st]); continue; }
                     if (rank == 0) mbar_arrive_expect_tx(&full[st], (uint32_t)(kStageBytes * G));
-                    if (G == 2) tma_load_2d_2sm(&tm_queue, mapa_shared(smem_u32(&full[st]), 0), b_s + (size_t)st * kStageBytes, kc * 64, brow);
-                    else        tma_load_2d(&tm_queue, &full[st], b_s + (size_t)st * kStageBytes, kc * 64, brow);
+                    if (G == 2) {
+                        tma_load_2d_2sm(&tm_queue, mapa_shared(smem_u32(&full[st]), 0), b_s + (size_t)st * kStageBytes, kc * 64, brow);
+                    } else if (CS > 1) {
+                        // this CTA's 1/CS of the tile rows, multicast into every CTA of the cluster
+                        constexpr int kPart = kStatsBN / CS;
+                        tma_load_2d_mc(&tm_queue, &full[st], b_s + (size_t)st * kStageBytes + (size_t)crank * kPart * 128,
+                                       kc * 64, brow + (int)crank * kPart, kMask);
+                    } else {
+                        tma_load_2d(&tm_queue, &full[st], b_s + (size_t)st * kStageBytes, kc * 64, brow);
+                    }
                 }
             }
         }
@@ -132,93 +151,114 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     const uint32_t b_addr = smem_u32(b_s + (size_t)st * kStageBytes);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
+                        if (a.debug & 2) break;
                         umma_ss<G>(d_tmem, make_sw128_desc(a_addr + k * 32, 0, 1024),
                                    make_sw128_desc(b_addr + k * 32, 0, 1024), idesc, (uint32_t)((kc | k) != 0));
                     }
-                    umma_commit<G>(&empty[st]);
+                    if (CS > 1) umma_commit_mc(&empty[st], kMask); else umma_commit<G>(&empty[st]);
                 }
                 umma_commit<G>(&tfull[acc]);
             }
         }
     } else if (warp >= 4) {
-        // ---------------------------------------------------- epilogue (8 warps)
+        // ---------------------------------------------------- epilogue (kEpiWarps warps)
+        // Warp w may only touch TMEM lanes 32*(w%4)..+31; the 16 warps form 4 column groups of kEpiCols
+        // accumulator columns each.  A thread owns one q row and kEpiCols columns per tile: it pulls them
+        // into registers with two tcgen05.ld, releases the accumulator buffer immediately (the MMA of tile
+        // t+2 can start while the exps of tile t are still being computed) and folds them into its
+        // running (max, sum) in the log2 domain.
         const int quarter = warp & 3;
-        const int half = (warp - 4) >> 2;
+        const int cgrp = (warp - 4) >> 2;
         const int row_local = quarter * 32 + lane;
         const int grow = row0 + row_local;
         const float scale2 = a.inv_T * kLog2e;
         float m = -INFINITY, s = 0.f;
         float* lrow = (a.logits != nullptr && grow < a.N) ? a.logits + (size_t)grow * (a.K + 1) + 1 : nullptr;
+        auto fold = [&](const uint32_t (&r)[32], int col0) {
+            const int valid = a.K - col0;
+            if (valid >= 32) {
+                float c0 = fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1]));
+                float c1 = fmaxf(__uint_as_float(r[2]), __uint_as_float(r[3]));
+#pragma unroll
+                for (int j = 4; j < 32; j += 4) {
+                    c0 = fmaxf(c0, fmaxf(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1])));
+                    c1 = fmaxf(c1, fmaxf(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+                }
+                const float cm = fmaxf(c0, c1) * scale2;
+                if (cm > m) { s *= ex2(m - cm); m = cm; }
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    s0 += ex2(fmaf(__uint_as_float(r[j + 0]), scale2, -m));
+                    s1 += ex2(fmaf(__uint_as_float(r[j + 1]), scale2, -m));
+                    s2 += ex2(fmaf(__uint_as_float(r[j + 2]), scale2, -m));
+                    s3 += ex2(fmaf(__uint_as_float(r[j + 3]), scale2, -m));
+                }
+                s += (s0 + s1) + (s2 + s3);
+                if (lrow) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) lrow[col0 + j] = __uint_as_float(r[j]) * a.inv_T;
+                }
+            } else if (valid > 0) {
+                float cm = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (j < valid) cm = fmaxf(cm, __uint_as_float(r[j]));
+                cm *= scale2;
+                if (cm > m) { s *= ex2(m - cm); m = cm; }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (j < valid) {
+                        s += ex2(fmaf(__uint_as_float(r[j]), scale2, -m));
+                        if (lrow) lrow[col0 + j] = __uint_as_float(r[j]) * a.inv_T;
+                    }
+                }
+            }
+        };
         int lt = 0;
         for (int t = t0; t < t1; ++t, ++lt) {
             const int acc = lt & 1;
             const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
             mbar_wait(&tfull[acc], aph);
             tc_fence_after();
+            const int col = cgrp * kEpiCols;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kStatsBN + col);
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-                const int col = half * 128 + ch * 32;
+            for (int ch = 0; ch < kEpiChunks; ++ch) {
                 uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kStatsBN + col), r);
+                tmem_ld32(taddr + (uint32_t)(ch * 32), r);
                 tmem_ld_wait();
-                const int col0 = t * kStatsBN + col;
-                const int valid = a.K - col0;
-                if (valid >= 32) {
-                    float cm = __uint_as_float(r[0]);
-#pragma unroll
-                    for (int j = 1; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(r[j]));
-                    cm *= scale2;
-                    if (cm > m) { s *= ex2(m - cm); m = cm; }
-                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        s0 += ex2(fmaf(__uint_as_float(r[j + 0]), scale2, -m));
-                        s1 += ex2(fmaf(__uint_as_float(r[j + 1]), scale2, -m));
-                        s2 += ex2(fmaf(__uint_as_float(r[j + 2]), scale2, -m));
-                        s3 += ex2(fmaf(__uint_as_float(r[j + 3]), scale2, -m));
-                    }
-                    s += (s0 + s1) + (s2 + s3);
-                    if (lrow) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) lrow[col0 + j] = __uint_as_float(r[j]) * a.inv_T;
-                    }
-                } else if (valid > 0) {
-                    float cm = -INFINITY;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (j < valid) cm = fmaxf(cm, __uint_as_float(r[j]));
-                    cm *= scale2;
-                    if (cm > m) { s *= ex2(m - cm); m = cm; }
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (j < valid) {
-                            s += ex2(fmaf(__uint_as_float(r[j]), scale2, -m));
-                            if (lrow) lrow[col0 + j] = __uint_as_float(r[j]) * a.inv_T;
-                        }
+                if (ch == kEpiChunks - 1) {
+                    // the whole accumulator slice of this warp is in registers: hand the buffer back to the MMA
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (G == 2) mbar_arrive_cluster(&tempty[acc], 0);
+                        else        mbar_arrive(&tempty[acc]);
                     }
                 }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (G == 2) mbar_arrive_cluster(&tempty[acc], 0);
-                else        mbar_arrive(&tempty[acc]);
+                if (!(a.debug & 1)) fold(r, t * kStatsBN + col + ch * 32);
             }
         }
-        // combine the two column halves of each row, then publish the slice partial
-        if (half == 1) red_s[row_local] = make_float2(m, s);
-        named_bar_sync(1, 256);
-        if (half == 0) {
-            float2 o = red_s[row_local];
-            float M = fmaxf(m, o.x);
-            float S = 0.f;
-            if (m != -INFINITY) S += s * ex2(m - M);
-            if (o.x != -INFINITY) S += o.y * ex2(o.x - M);
+        // combine the column groups of each row (fixed order), then publish the slice partial
+        if (cgrp > 0) red_s[(cgrp - 1) * kRowsPerCta + row_local] = make_float2(m, s);
+        named_bar_sync(1, kEpiWarps * 32);
+        if (cgrp == 0) {
+            float M = m;
+#pragma unroll
+            for (int gq = 0; gq < kEpiWarps / 4 - 1; ++gq) M = fmaxf(M, red_s[gq * kRowsPerCta + row_local].x);
+            float S = (m != -INFINITY) ? s * ex2(m - M) : 0.f;
+#pragma unroll
+            for (int gq = 0; gq < kEpiWarps / 4 - 1; ++gq) {
+                float2 o = red_s[gq * kRowsPerCta + row_local];
+                if (o.x != -INFINITY) S += o.y * ex2(o.x - M);
+            }
             a.part_ms[(size_t)slice * a.n_pad + grow] = make_float2(M, S);
         }
     }
 
+    __syncwarp();
     tc_fence_before();
-    if (G == 2) cluster_sync_all(); else __syncthreads();
+    if (kClustered) cluster_sync_all(); else __syncthreads();
     if (warp == 2) tmem_dealloc<G>(tmem_base, 512);
 }
 
@@ -236,6 +276,7 @@ struct DqArgs {
     float* part_o;        // [slices, n_pad, C]
 };
 
+template <int CS>
 __global__ void __launch_bounds__(kDqThreads, 1)
 nce_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_queue,
               const DqArgs a) {
@@ -259,8 +300,13 @@ nce_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mblk = blockIdx.x % a.mblks;
-    const int slice = blockIdx.x / a.mblks;
+    constexpr bool kClustered = CS > 1;
+    constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
+    const uint32_t crank = kClustered ? cluster_ctarank() : 0u;
+    const int cluster_id = blockIdx.x / CS;
+    const int mgroups = a.mblks / CS;                           // host guarantees CS | mblks
+    const int mblk = (cluster_id % mgroups) * CS + (int)crank;
+    const int slice = cluster_id / mgroups;
     const int t0 = (int)(((long long)slice * a.num_tiles) / a.slices);
     const int t1 = (int)(((long long)(slice + 1) * a.num_tiles) / a.slices);
     const int ntiles = t1 - t0;
@@ -273,7 +319,7 @@ nce_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         tma_prefetch_desc(&tm_queue);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], CS); }
         for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 8); }
         mbar_init(p_full, 8);
         mbar_init(p_empty, 1);
@@ -286,7 +332,7 @@ nce_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         tmem_relinquish<1>();
     }
     tc_fence_before();
-    __syncthreads();
+    if (kClustered) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -300,9 +346,17 @@ nce_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                 const uint32_t ph = (uint32_t)(i / NS) & 1u;
                 mbar_wait(&kv_empty[st], ph ^ 1u);
                 mbar_arrive_expect_tx(&kv_full[st], (uint32_t)tile_bytes);
-                for (int kc = 0; kc < kchunks; ++kc)
-                    tma_load_2d(&tm_queue, &kv_full[st], v_s + (size_t)st * tile_bytes + kc * kSlab, kc * 64,
-                                (t0 + i) * kDqBN);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    if (CS > 1) {
+                        constexpr int kPart = kDqBN / CS;      // this CTA's rows of the tile, multicast to the cluster
+                        tma_load_2d_mc(&tm_queue, &kv_full[st],
+                                       v_s + (size_t)st * tile_bytes + kc * kSlab + (size_t)crank * kPart * 128, kc * 64,
+                                       (t0 + i) * kDqBN + (int)crank * kPart, kMask);
+                    } else {
+                        tma_load_2d(&tm_queue, &kv_full[st], v_s + (size_t)st * tile_bytes + kc * kSlab, kc * 64,
+                                    (t0 + i) * kDqBN);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -347,7 +401,7 @@ nce_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                                make_sw128_desc(v_addr + kk * 2048, kSlab, 1024), idesc_o,
                                (uint32_t)((i | kk) != 0));
                 }
-                umma_commit<1>(&kv_empty[st]);
+                if (CS > 1) umma_commit_mc(&kv_empty[st], kMask); else umma_commit<1>(&kv_empty[st]);
                 umma_commit<1>(p_empty);
             }
             umma_commit<1>(o_full);
@@ -416,83 +470,29 @@ nce_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         }
     }
 
+    __syncwarp();
     tc_fence_before();
-    __syncthreads();
+    if (kClustered) cluster_sync_all(); else __syncthreads();
     if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
 // =====================================================================================
 // Host side
 // =====================================================================================
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn) return fn;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess || p == nullptr)
-        return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-    return fn;
-}
-
-// [rows, C] bf16 row-major tensor, box = [box_rows, 64 elements], 128B swizzle, OOB -> zeros.
-static bool make_tmap(CUtensorMap* m, const void* base, int rows, int C, int box_rows) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
-    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return false; }
-    return true;
-}
-
-template <typename Kern, typename Args>
-static cudaError_t launch_cluster(Kern kern, int grid, int threads, int smem, int cluster, cudaStream_t stream,
-                                  const CUtensorMap& a, const CUtensorMap& b, const Args& args) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(threads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, a, b, args);
-}
-
 cudaError_t launch_nce_tc(NceTcParams& p, const NceWorkspace& ws, cudaStream_t stream) {
     if (p.C % 64 != 0 || p.C < 64 || p.C > 256 || p.N < 1 || p.K < 1) return cudaErrorNotSupported;
     const int G = p.cta_group;
     const int kchunks = p.C / 64;
     const int mblks = (p.N + 128 * G - 1) / (128 * G);
-    const int clusters_avail = p.num_sms / G;
-    if (mblks > clusters_avail) return cudaErrorNotSupported;
+    const int CS = (G == 1) ? pick_share(mblks, p.max_share) : 1;
+    if (mblks * G > p.num_sms) return cudaErrorNotSupported;
     const int num_tiles = (p.K + kStatsBN - 1) / kStatsBN;
-    int slices = clusters_avail / mblks;
-    if (slices > num_tiles) slices = num_tiles;
     const int n_pad = mblks * G * 128;
-    if ((size_t)slices * n_pad > (size_t)kMaxCtas * kRowsPerCta) return cudaErrorNotSupported;
-    p.slices = slices;
     p.n_pad = n_pad;
 
     CUtensorMap tm_q, tm_queue;
     if (!make_tmap(&tm_q, p.q_bf16, p.N, p.C, 128)) return cudaErrorUnknown;
-    if (!make_tmap(&tm_queue, p.queue, p.K, p.C, kStatsBN / G)) return cudaErrorUnknown;
+    if (!make_tmap(&tm_queue, p.queue, p.K, p.C, kStatsBN / (G * CS))) return cudaErrorUnknown;
 
     const int stage_bytes = (kStatsBN / G) * 128;
     const int fixed = kchunks * kSlab + 4096;     // q tile + barriers/red_s
@@ -503,33 +503,42 @@ cudaError_t launch_nce_tc(NceTcParams& p, const NceWorkspace& ws, cudaStream_t s
 
     StatsArgs a;
     a.N = p.N; a.C = p.C; a.K = p.K;
-    a.mblks = mblks; a.slices = slices; a.n_pad = n_pad; a.num_tiles = num_tiles; a.stages = stages;
+    a.mblks = mblks; a.slices = 0; a.n_pad = n_pad; a.num_tiles = num_tiles; a.stages = stages;
     a.inv_T = p.inv_T;
     a.logits = p.logits;
     a.part_ms = ws.part_ms;
-    const int grid = mblks * slices * G;
-    if (G == 2) return launch_cluster(nce_stats_kernel<2>, grid, kStatsThreads, smem, 2, stream, tm_q, tm_queue, a);
-    return launch_cluster(nce_stats_kernel<1>, grid, kStatsThreads, smem, 1, stream, tm_q, tm_queue, a);
+    a.debug = debug_mode();
+    auto fill = [](StatsArgs& x, int slices) { x.slices = slices; };
+    static KernelCache kc[4];
+    const int mgroups = mblks / CS, per_slice = mblks * G;
+    if (G == 2)
+        return plan_and_launch(nce_stats_kernel<2, 1>, kc[0], kStatsThreads, smem, 2, mgroups, per_slice, num_tiles,
+                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
+    if (CS == 4)
+        return plan_and_launch(nce_stats_kernel<1, 4>, kc[1], kStatsThreads, smem, 4, mgroups, per_slice, num_tiles,
+                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
+    if (CS == 2)
+        return plan_and_launch(nce_stats_kernel<1, 2>, kc[2], kStatsThreads, smem, 2, mgroups, per_slice, num_tiles,
+                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
+    return plan_and_launch(nce_stats_kernel<1, 1>, kc[3], kStatsThreads, smem, 1, mgroups, per_slice, num_tiles, n_pad,
+                           &p.slices, stream, tm_q, tm_queue, a, fill);
 }
 
 cudaError_t launch_nce_dq_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* queue, int N, int C, int K,
-                             float inv_T, const float* lse, int num_sms, int* slices_out, int* n_pad_out,
-                             const NceWorkspace& ws, cudaStream_t stream) {
+                             float inv_T, const float* lse, int num_sms, int max_share, int* slices_out,
+                             int* n_pad_out, const NceWorkspace& ws, cudaStream_t stream) {
     if (C % 64 != 0 || C < 64 || C > 256) return cudaErrorNotSupported;
     const int kchunks = C / 64;
     const int mblks = (N + 127) / 128;
+    const int CS = pick_share(mblks, max_share);
     if (mblks > num_sms) return cudaErrorNotSupported;
     const int num_tiles = (K + kDqBN - 1) / kDqBN;
-    int slices = num_sms / mblks;
-    if (slices > num_tiles) slices = num_tiles;
     const int n_pad = mblks * 128;
-    if ((size_t)slices * n_pad > (size_t)kMaxCtas * kRowsPerCta) return cudaErrorNotSupported;
-    *slices_out = slices;
     *n_pad_out = n_pad;
 
     CUtensorMap tm_q, tm_queue;
     if (!make_tmap(&tm_q, q_bf16, N, C, 128)) return cudaErrorUnknown;
-    if (!make_tmap(&tm_queue, queue, K, C, kDqBN)) return cudaErrorUnknown;
+    if (!make_tmap(&tm_queue, queue, K, C, kDqBN / CS)) return cudaErrorUnknown;
 
     const int tile_bytes = kchunks * kSlab;
     const int fixed = tile_bytes + 2 * kSlab + 1024;      // q + P + barriers
@@ -540,11 +549,21 @@ cudaError_t launch_nce_dq_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* q
 
     DqArgs a;
     a.N = N; a.C = C; a.K = K;
-    a.mblks = mblks; a.slices = slices; a.n_pad = n_pad; a.num_tiles = num_tiles; a.stages = stages;
+    a.mblks = mblks; a.slices = 0; a.n_pad = n_pad; a.num_tiles = num_tiles; a.stages = stages;
     a.inv_T = inv_T;
     a.lse = lse;
     a.part_o = ws.part_o;
-    return launch_cluster(nce_dq_kernel, mblks * slices, kDqThreads, smem, 1, stream, tm_q, tm_queue, a);
+    auto fill = [](DqArgs& x, int slices) { x.slices = slices; };
+    static KernelCache kc[3];
+    const int mgroups = mblks / CS;
+    if (CS == 4)
+        return plan_and_launch(nce_dq_kernel<4>, kc[0], kDqThreads, smem, 4, mgroups, mblks, num_tiles, n_pad,
+                               slices_out, stream, tm_q, tm_queue, a, fill);
+    if (CS == 2)
+        return plan_and_launch(nce_dq_kernel<2>, kc[1], kDqThreads, smem, 2, mgroups, mblks, num_tiles, n_pad,
+                               slices_out, stream, tm_q, tm_queue, a, fill);
+    return plan_and_launch(nce_dq_kernel<1>, kc[2], kDqThreads, smem, 1, mgroups, mblks, num_tiles, n_pad, slices_out,
+                           stream, tm_q, tm_queue, a, fill);
 }
 
 }  // namespace moco

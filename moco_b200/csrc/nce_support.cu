@@ -99,11 +99,11 @@ __global__ void combine_kernel(int N, int C, int K, int slices, int n_pad, float
                                float* __restrict__ lse, float* __restrict__ loss_rows,
                                float* __restrict__ prob_rows, float* __restrict__ loss_prob,
                                unsigned int* __restrict__ counters) {
-    const int i = blockIdx.x;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp per q row
     const float scale2 = inv_T * kLog2e;
-    const float x0 = lpos[i] * scale2;             // positive logit, log2 domain
-    if (threadIdx.x < 32) {
-        int lane = threadIdx.x;
+    if (i < N) {
+        const float x0 = lpos[i] * scale2;         // positive logit, log2 domain
+        int lane = threadIdx.x & 31;
         float m = x0;
         for (int s = lane; s < slices; s += 32) m = fmaxf(m, part_ms[(size_t)s * n_pad + i].x);
         m = warp_max(m);
@@ -131,8 +131,9 @@ __global__ void combine_kernel(int N, int C, int K, int slices, int n_pad, float
 cudaError_t launch_combine(int N, int C, int slices, int n_pad, float inv_T, float* logits, int K, float* lse,
                            float* loss_rows, float* prob_rows, float* loss_prob, const NceWorkspace& ws,
                            cudaStream_t stream) {
-    combine_kernel<<<N, 32, 0, stream>>>(N, C, K, slices, n_pad, inv_T, ws.lpos, ws.part_ms, logits, lse,
-                                         loss_rows, prob_rows, loss_prob, ws.counters);
+    const int rows_per_block = 8;
+    combine_kernel<<<(N + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, stream>>>(
+        N, C, K, slices, n_pad, inv_T, ws.lpos, ws.part_ms, logits, lse, loss_rows, prob_rows, loss_prob, ws.counters);
     return cudaGetLastError();
 }
 
@@ -140,21 +141,43 @@ cudaError_t launch_combine(int N, int C, int slices, int n_pad, float inv_T, flo
 __global__ void dq_reduce_kernel(int N, int C, int slices, int n_pad, float inv_T, const void* __restrict__ k,
                                  int k_dtype, const float* __restrict__ part_o,
                                  const float* __restrict__ prob_rows, float* __restrict__ dq) {
+    // 256 threads = (C/4 float4 lanes) x groups; group g sums slices g, g+groups, ...; groups are then
+    // added in index order (deterministic).
+    __shared__ float4 s_part[256];
     const int i = blockIdx.x;
-    const float gscale = inv_T / (float)N;
-    const float pm1 = prob_rows[i] - 1.f;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float acc = 0.f;
-        for (int s = 0; s < slices; ++s) acc += part_o[((size_t)s * n_pad + i) * C + c];
-        float kv = load_as_float(k, k_dtype, (size_t)i * C + c);
-        dq[(size_t)i * C + c] = gscale * (acc + pm1 * kv);
+    const int lanes = C >> 2;
+    const int groups = 256 / lanes;
+    const int lane = threadIdx.x % lanes, grp = threadIdx.x / lanes;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (grp < groups) {
+        for (int s = grp; s < slices; s += groups) {
+            float4 v = __ldcs(reinterpret_cast<const float4*>(part_o + ((size_t)s * n_pad + i) * C) + lane);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        s_part[grp * lanes + lane] = acc;
+    }
+    __syncthreads();
+    if (grp == 0) {
+        for (int g = 1; g < groups; ++g) {
+            float4 v = s_part[g * lanes + lane];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        const float gscale = inv_T / (float)N;
+        const float pm1 = prob_rows[i] - 1.f;
+        const size_t base = (size_t)i * C + lane * 4;
+        float4 o;
+        o.x = gscale * (acc.x + pm1 * load_as_float(k, k_dtype, base + 0));
+        o.y = gscale * (acc.y + pm1 * load_as_float(k, k_dtype, base + 1));
+        o.z = gscale * (acc.z + pm1 * load_as_float(k, k_dtype, base + 2));
+        o.w = gscale * (acc.w + pm1 * load_as_float(k, k_dtype, base + 3));
+        *reinterpret_cast<float4*>(dq + base) = o;
     }
 }
 
 cudaError_t launch_dq_reduce(int N, int C, int slices, int n_pad, float inv_T, const void* k, int k_dtype,
                              const float* prob_rows, float* dq, const NceWorkspace& ws, cudaStream_t stream) {
-    int threads = C >= 256 ? 256 : (C + 31) / 32 * 32;
-    dq_reduce_kernel<<<N, threads, 0, stream>>>(N, C, slices, n_pad, inv_T, k, k_dtype, ws.part_o, prob_rows, dq);
+    if ((C & 3) != 0 || C > 1024) return cudaErrorNotSupported;
+    dq_reduce_kernel<<<N, 256, 0, stream>>>(N, C, slices, n_pad, inv_T, k, k_dtype, ws.part_o, prob_rows, dq);
     return cudaGetLastError();
 }
 

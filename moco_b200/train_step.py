@@ -36,7 +36,7 @@ class MoCoStep:
             # ShuffleBN forward (train.py:258) on the side stream while the query encoder runs
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side), torch.no_grad():
-                x2_shuffled, backward_inds = DistributedShufle.forward_shuffle(x2, epoch)
+                x2_shuffled, backward_inds = DistributedShufle.forward_shuffle(x2, epoch, cast_dtype=self.amp_dtype)
             x2.record_stream(self.side)
         with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
             feat_q = self.model(x1)                                                  # train.py:256
@@ -45,7 +45,7 @@ class MoCoStep:
                 main.wait_stream(self.side)
                 x2_shuffled.record_stream(main)
             else:
-                x2_shuffled, backward_inds = DistributedShufle.forward_shuffle(x2, epoch)
+                x2_shuffled, backward_inds = DistributedShufle.forward_shuffle(x2, epoch, cast_dtype=self.amp_dtype)
             with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
                 feat_k = self.model_ema(x2_shuffled)                                 # train.py:259
             feat_k_all, feat_k = DistributedShufle.backward_shuffle(feat_k, backward_inds, return_local=True)

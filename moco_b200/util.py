@@ -141,21 +141,27 @@ class ShuffleContext:
         _lib.check(lib.moco_signal_barrier(self.pad.table, self.world, self.rank, self.epoch, _lib.cur_stream()),
                    "moco_signal_barrier")
 
-    def gather(self, kind: str, x: torch.Tensor, src_rows: torch.Tensor) -> torch.Tensor:
-        """out[i] = (rank-major concatenation of every rank's x)[src_rows[i]]."""
+    def gather(self, kind: str, x: torch.Tensor, src_rows: torch.Tensor, cast_dtype=None) -> torch.Tensor:
+        """out[i] = (rank-major concatenation of every rank's x)[src_rows[i]].
+
+        cast_dtype (world > 1 only): publish the batch in this dtype -- the cast is fused into the copy
+        into the peer-visible staging buffer, so e.g. fp32 images cross NVLink as bf16 (what the autocast
+        key encoder would round them to anyway)."""
         lib = _lib.load()
         _lib.require_cuda(x, src_rows)
         x = x.contiguous()
         n = x.shape[0]
-        row_bytes = x[0].numel() * x.element_size() if n else 0
+        dtype = cast_dtype if (cast_dtype is not None and self.world > 1) else x.dtype
+        esize = torch.empty((), dtype=dtype).element_size()
+        row_bytes = x[0].numel() * esize if n else 0
         if row_bytes % 16 != 0:
             raise ValueError(f"moco_b200 shuffle: row size {row_bytes} B is not a multiple of 16")
-        out = torch.empty((src_rows.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        out = torch.empty((src_rows.shape[0],) + tuple(x.shape[1:]), dtype=dtype, device=x.device)
         if self.world == 1:
             table = (ctypes.c_void_p * 1)(x.data_ptr())
         else:
-            buf = self._staging(kind, x.numel() * x.element_size())
-            stage = buf.tensor(x.shape, x.dtype)
+            buf = self._staging(kind, x.numel() * esize)
+            stage = buf.tensor(x.shape, dtype)
             if stage.data_ptr() != x.data_ptr():
                 stage.copy_(x)
             self.barrier()           # every rank's staging buffer is complete and visible
@@ -182,13 +188,14 @@ def dist_collect(x):
 
 class DistributedShufle:
     @staticmethod
-    def forward_shuffle(x, epoch):
+    def forward_shuffle(x, epoch, cast_dtype=None):
         """forward shuffle, return shuffled batch of x from all processes (util.py:69-79).
-        epoch is used as manual seed to make sure the shuffle id in all process is same."""
+        epoch is used as manual seed to make sure the shuffle id in all process is same.
+        cast_dtype: optional extension, see ShuffleContext.gather."""
         rank, world = _world()
         forward_inds, backward_inds = DistributedShufle.get_shuffle_ids(x.shape[0] * world, epoch, x.device)
         forward_inds_local = DistributedShufle.get_local_id(forward_inds)
-        return ShuffleContext.get().gather("fwd", x, forward_inds_local), backward_inds
+        return ShuffleContext.get().gather("fwd", x, forward_inds_local, cast_dtype), backward_inds
 
     @staticmethod
     def backward_shuffle(x, backward_inds, return_local=True):

@@ -14,7 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-FLAGS = {"auto": 0, "simt": 1, "tc2": 2, "tc1": 4}
+FLAGS = {"auto": 0, "simt": 1, "tc2": 2, "tc1": 4, "tc1_nomc": 4, "tc1_s2": 12, "tc1_s4": 20, "dq2": 36, "dq2_nomc": 36, "dq2_s2": 44, "dq2_s4": 52}
 
 # name: (N, C, K, T, flagname, want_logits, timing_iters)
 NCE_CASES = {
@@ -30,6 +30,22 @@ NCE_CASES = {
     "tc1_c5": (512, 256, 262144, 0.07, "tc1", False, 10),
     "tc2_c5": (512, 256, 262144, 0.07, "tc2", False, 10),
     "tc1_c3_dense": (256, 128, 65536, 0.07, "tc1", True, 5),
+    "nomc_c5": (512, 256, 262144, 0.07, "tc1_nomc", False, 10),
+    "s4_c5": (512, 256, 262144, 0.07, "tc1_s4", False, 10),
+    "nomc_c3": (256, 128, 65536, 0.07, "tc1_nomc", False, 20),
+    "tc1_c4": (2048, 128, 16384, 0.07, "tc1", False, 20),
+    "s4_c4": (2048, 128, 16384, 0.07, "tc1_s4", False, 20),
+    "s4_ragged": (500, 192, 3000, 0.1, "tc1_s4", True, 0),
+    "tc1_ragged2": (300, 64, 5000, 0.1, "tc1", True, 0),
+    "dq2_small": (32, 128, 1024, 0.07, "dq2", False, 0),
+    "dq2_c64": (100, 64, 777, 0.07, "dq2", False, 0),
+    "dq2_ragged": (200, 192, 1000, 0.1, "dq2", False, 0),
+    "dq2_s4_ragged": (500, 256, 3000, 0.1, "dq2_s4", False, 0),
+    "dq2_c2": (256, 128, 16384, 0.07, "dq2", False, 20),
+    "dq2_c3": (256, 128, 65536, 0.07, "dq2", False, 20),
+    "dq2_c4": (2048, 128, 16384, 0.07, "dq2", False, 20),
+    "dq2_c5": (512, 256, 262144, 0.07, "dq2", False, 10),
+    "dq2_nomc_c5": (512, 256, 262144, 0.07, "dq2_nomc", False, 10),
 }
 
 
@@ -100,8 +116,22 @@ def run_nce(name):
             e1.record()
             torch.cuda.synchronize()
             out[tag] = e0.elapsed_time(e1) * 1e3 / iters
-        out["fwd_tflops"] = 2.0 * N * C * K / (out["fwd_us"] * 1e-6) / 1e12
-        out["dq_tflops"] = 4.0 * N * C * K / ((out["fwd_dq_us"] - out["fwd_us"]) * 1e-6) / 1e12
+        # per-kernel device time via the library's profiling hook (events right around one kernel)
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(iters)]
+        for e4 in ev:
+            for e in e4:
+                e.record()
+        for i in range(iters):
+            lib.moco_prof_set_events(1, ev[i][0].cuda_event, ev[i][1].cuda_event)
+            lib.moco_prof_set_events(2, ev[i][2].cuda_event, ev[i][3].cuda_event)
+            call(True)
+        lib.moco_prof_set_events(1, None, None)
+        lib.moco_prof_set_events(2, None, None)
+        torch.cuda.synchronize()
+        out["stats_kernel_us"] = sum(e[0].elapsed_time(e[1]) for e in ev) * 1e3 / iters
+        out["dq_kernel_us"] = sum(e[2].elapsed_time(e[3]) for e in ev) * 1e3 / iters
+        out["stats_tflops"] = 2.0 * N * C * K / (out["stats_kernel_us"] * 1e-6) / 1e12
+        out["dq_tflops"] = 4.0 * N * C * K / (out["dq_kernel_us"] * 1e-6) / 1e12
     return out
 
 
@@ -205,12 +235,15 @@ CASES = {**{n: run_nce for n in NCE_CASES}, "enqueue": run_enqueue, "gather": ru
 
 
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] != "--all":
+    if len(sys.argv) == 2 and sys.argv[1] != "--all":
         name = sys.argv[1]
         print(json.dumps(CASES[name](name)))
         return
-    order = ["enqueue", "gather", "simt_small", "tc1_small", "tc2_small", "tc1_ragged", "tc2_ragged", "module",
-             "tc1_c2", "tc2_c2", "tc1_c3", "tc2_c3", "tc1_c5", "tc2_c5", "tc1_c3_dense"]
+    order = ["enqueue", "gather", "simt_small", "tc1_small", "tc2_small", "tc1_ragged", "tc2_ragged", "s4_ragged",
+             "tc1_ragged2", "module", "tc1_c2", "tc2_c2", "tc1_c3", "nomc_c3", "tc2_c3", "tc1_c4", "s4_c4",
+             "tc1_c5", "nomc_c5", "s4_c5", "tc2_c5", "tc1_c3_dense"]
+    if len(sys.argv) > 2:
+        order = sys.argv[1:]
     for name in order:
         t0 = time.time()
         try:
