@@ -43,6 +43,11 @@ def parse():
     return ap.parse_args()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of nce_stats_kernel from the committed
+# `ncu --set full` captures (profiles/r1_nce_c2_ncu_metrics.csv, profiles/r1_nce_c5_ncu_metrics.csv)
+NCU_TRAFFIC_BYTES = {(256, 128, 16384): 4286976, (512, 256, 262144): 134530048 + 3916544}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -160,7 +165,8 @@ def stress_roofline(peaks, dev):
     return {
         "workload": "BASELINE configs[4]: N=512 feat_dim=256 K=262144 (stats kernel alone, queue 134 MB > L2)",
         "bound": "tensor", "achieved": a, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": a / peaks["tf_burst"],
-        "us_per_launch": us_stats, "hbm_GBps": bytes_ / (us_stats * 1e-6) / 1e9, "traffic": None,
+        "us_per_launch": us_stats, "hbm_GBps": bytes_ / (us_stats * 1e-6) / 1e9,
+        "traffic": NCU_TRAFFIC_BYTES.get((N, C, K)),
         "dq_kernel": {"achieved": a_dq, "unit": "TFLOP/s", "frac": a_dq / peaks["tf_burst"], "us_per_launch": us_dq,
                       "flops_counted": "4*N*C*K (S recompute + P.Queue, both executed on tcgen05)"},
     }
@@ -304,7 +310,7 @@ def run_native(args):
         "frac": a_tf / peaks["tf_sustained"], "peak_source": peaks["source"] + ", sustained bf16",
         "us_per_launch": us_stats, "algorithmic_flops": flops, "algorithmic_bytes": bytes_,
         "hbm_GBps": bytes_ / (us_stats * 1e-6) / 1e9, "hbm_frac": bytes_ / (us_stats * 1e-6) / 1e9 / peaks["hbm_gbs"],
-        "traffic": None,
+        "traffic": NCU_TRAFFIC_BYTES.get((N, C, K)),
         "dq_kernel": {"us_per_launch": us_dq, "achieved": 2 * flops / (us_dq * 1e-6) / 1e12, "unit": "TFLOP/s",
                       "frac": 2 * flops / (us_dq * 1e-6) / 1e12 / peaks["tf_sustained"]},
         "note": "ideal time for this config is < 1 us (1.07 GFLOP / 4.2 MB): launch + pipeline fill bound; "

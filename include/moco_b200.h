@@ -118,6 +118,42 @@ int moco_queue_enqueue(void* queue_bf16, float* queue_f32_or_null,
                        const void* k_all, int k_dtype, int n_all, int C, int64_t K,
                        int64_t index, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Sharded queue (BASELINE configs[3]): rank r keeps rows
+ * [r*K/W, (r+1)*K/W) of the K-row ring ("block" layout) instead of a replica.
+ * Every rank evaluates ALL W*N queries against its shard; two small collectives
+ * (done by the caller with NCCL) stitch the softmax together:
+ *
+ *   moco_nce_shard_stats : q_all, k_all [Nq, C] (Nq = W*N, rank-major), shard [Ks, C]
+ *                          -> ms_out[Nq] float2 = per-row (max, sum 2^(x-max)) over the shard, log2 domain;
+ *                          also leaves <q_i, k_i> and bf16(q_all) in the workspace
+ *   ... all_gather ms_out -> ms_all [W, Nq] ...
+ *   moco_nce_shard_merge : ms_all + the positive logit -> lse / loss_rows / prob_rows for all Nq rows
+ *                          (same workspace as the stats call); loss_prob = means over all Nq rows
+ *   moco_nce_shard_dq    : o_partial[Nq, C] = sum_{j in shard} exp(x_ij - lse_i) * shard_j
+ *   ... reduce_scatter o_partial -> o_own [N, C] ...
+ *   moco_nce_shard_dq_finish : dq_i = inv_T / N * (o_own_i + (prob_i - 1) * k_i)
+ *
+ * The loss is permutation-invariant over negatives, so it equals the replicated
+ * reference's; ring slot g of moco/NCE/Contrast.py:32 maps to (rank g / (K/W),
+ * local row g % (K/W)) -- moco_queue_enqueue_shard writes only the slots this
+ * rank owns, so indices stay checkable bit-exactly against the reference's.
+ * ---------------------------------------------------------------------- */
+int moco_nce_shard_stats(const void* q_all, const void* k_all, int qk_dtype, const void* shard_bf16,
+                         int Nq, int C, int Ks, float inv_T, void* ms_out,
+                         void* workspace, size_t workspace_bytes, int flags, void* stream);
+int moco_nce_shard_merge(const void* ms_all, int world, int Nq, int C, float inv_T,
+                         float* lse, float* loss_rows, float* prob_rows, float* loss_prob,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int moco_nce_shard_dq(const void* q_all, int q_dtype, const void* shard_bf16, const float* lse_all,
+                      int Nq, int C, int Ks, float inv_T, float* o_partial,
+                      void* workspace, size_t workspace_bytes, int flags, void* stream);
+int moco_nce_shard_dq_finish(const float* o_own, const void* k_own, int k_dtype,
+                             const float* prob_rows_own, int N, int C, float inv_T, float* dq, void* stream);
+int moco_queue_enqueue_shard(void* shard_bf16, float* shard_f32_or_null, const void* k_all, int k_dtype,
+                             int n_all, int C, int64_t K, int64_t index,
+                             int64_t shard_row0, int64_t shard_rows, void* stream);
+
 /* fp32 -> bf16 (round-to-nearest-even); used to (re)build the bf16 working queue
  * from the fp32 `memory` buffer (init / load_state_dict). */
 int moco_f32_to_bf16(const float* src, void* dst_bf16, size_t n_elems, void* stream);

@@ -29,6 +29,15 @@ SIGNATURES = {
     "moco_nce_bwd_dense": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
                                    c_void_p, c_void_p]),
     "moco_queue_enqueue": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_void_p]),
+    "moco_nce_shard_stats": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
+                                     c_void_p, c_size_t, c_int, c_void_p]),
+    "moco_nce_shard_merge": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_size_t, c_void_p]),
+    "moco_nce_shard_dq": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
+                                  c_void_p, c_size_t, c_int, c_void_p]),
+    "moco_nce_shard_dq_finish": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "moco_queue_enqueue_shard": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64,
+                                         c_int64, c_int64, c_void_p]),
     "moco_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "moco_shuffle_gather": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p]),
     "moco_signal_barrier": (c_int, [POINTER(c_void_p), c_int, c_int, c_uint32, c_void_p]),
@@ -77,7 +86,8 @@ launches = 0
 class _Counting:
     """Thin proxy over the CDLL that counts this library's kernel launches."""
 
-    _PER_CALL = {"moco_queue_enqueue": 1, "moco_f32_to_bf16": 1, "moco_shuffle_gather": 1,
+    _PER_CALL = {"moco_nce_shard_stats": 3, "moco_nce_shard_merge": 1, "moco_nce_shard_dq": 2,
+                 "moco_nce_shard_dq_finish": 1, "moco_queue_enqueue_shard": 1, "moco_queue_enqueue": 1, "moco_f32_to_bf16": 1, "moco_shuffle_gather": 1,
                  "moco_signal_barrier": 1, "moco_nce_bwd_dense": 1}
 
     def __init__(self, lib):

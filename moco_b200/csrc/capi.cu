@@ -134,7 +134,7 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
                     e = launch_nce_dq_tc(qb, queue, N, C, K, inv_T, lse, d.sms, max_share, &slices, &n_pad, ws, stream);
                 prof_mark(MOCO_PROF_DQ, 1, stream);
                 if (e != cudaSuccess) return cuda_fail("tcgen05 dq kernel", e);
-                e = launch_dq_reduce(N, C, slices, n_pad, inv_T, k, qk_dtype, prob_rows, dq, ws, stream);
+                e = launch_dq_reduce(N, C, slices, n_pad, inv_T, k, qk_dtype, prob_rows, dq, ws.part_o, stream);
                 if (e != cudaSuccess) return cuda_fail("dq reduce kernel", e);
             }
             return MOCO_OK;
@@ -181,8 +181,119 @@ int moco_queue_enqueue(void* queue_bf16, float* queue_f32, const void* k_all, in
         return MOCO_ERR_INVALID;
     }
     cudaError_t e = launch_enqueue(static_cast<__nv_bfloat16*>(queue_bf16), queue_f32, k_all, k_dtype, n_all, C, K,
-                                   index, static_cast<cudaStream_t>(stream_));
+                                   index, 0, K, static_cast<cudaStream_t>(stream_));
     if (e != cudaSuccess) return cuda_fail("enqueue kernel", e);
+    return MOCO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Sharded queue (BASELINE configs[3]): every rank holds rows [shard_row0, shard_row0 + shard_rows) of the ring
+// ---------------------------------------------------------------------------------------------------------
+int moco_queue_enqueue_shard(void* shard_bf16, float* shard_f32, const void* k_all, int k_dtype, int n_all, int C,
+                             int64_t K, int64_t index, int64_t shard_row0, int64_t shard_rows, void* stream_) {
+    g_err[0] = 0;
+    if (!shard_bf16 || !k_all || n_all < 0 || C <= 0 || K <= 0 || index < 0 || index >= K || n_all > K ||
+        shard_row0 < 0 || shard_rows <= 0 || shard_row0 + shard_rows > K) {
+        set_error("moco_queue_enqueue_shard: bad argument");
+        return MOCO_ERR_INVALID;
+    }
+    cudaError_t e = launch_enqueue(static_cast<__nv_bfloat16*>(shard_bf16), shard_f32, k_all, k_dtype, n_all, C, K,
+                                   index, shard_row0, shard_rows, static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return cuda_fail("enqueue kernel", e);
+    return MOCO_OK;
+}
+
+static int shard_common(const char* what, const void* q, int N, int C, int Ks, void* workspace, size_t bytes,
+                        NceWorkspace* ws, DevInfo* d) {
+    if (!q || !workspace || N <= 0 || C <= 0 || Ks <= 0 || (reinterpret_cast<uintptr_t>(workspace) & 255)) {
+        set_error("%s: bad argument", what);
+        return MOCO_ERR_INVALID;
+    }
+    *ws = carve_workspace(workspace, N, C);
+    if (bytes < ws->bytes) { set_error("%s: workspace too small (%zu < %zu)", what, bytes, ws->bytes); return MOCO_ERR_WORKSPACE; }
+    *d = device_info();
+    if (!d->ok || d->major != 10 || C % 64 != 0 || C > 256) {
+        set_error("%s: needs an sm_100 device and C %% 64 == 0, C <= 256 (C=%d)", what, C);
+        return MOCO_ERR_UNSUPPORTED;
+    }
+    return MOCO_OK;
+}
+
+int moco_nce_shard_stats(const void* q_all, const void* k_all, int qk_dtype, const void* shard_bf16, int N, int C,
+                         int Ks, float inv_T, void* ms_out, void* workspace, size_t workspace_bytes, int flags,
+                         void* stream_) {
+    g_err[0] = 0;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NceWorkspace ws; DevInfo d;
+    int rc = shard_common("moco_nce_shard_stats", q_all, N, C, Ks, workspace, workspace_bytes, &ws, &d);
+    if (rc != MOCO_OK) return rc;
+    if (!k_all || !shard_bf16 || !ms_out) { set_error("moco_nce_shard_stats: null pointer"); return MOCO_ERR_INVALID; }
+    cudaError_t e = launch_prep(q_all, k_all, qk_dtype, N, C, ws, stream);
+    if (e != cudaSuccess) return cuda_fail("prep kernel", e);
+    NceTcParams p;
+    p.q_bf16 = qk_dtype == MOCO_BF16 ? static_cast<const __nv_bfloat16*>(q_all) : ws.q_bf16;
+    p.queue = static_cast<const __nv_bfloat16*>(shard_bf16);
+    p.N = N; p.C = C; p.K = Ks; p.inv_T = inv_T; p.logits = nullptr;
+    p.cta_group = (flags & MOCO_NCE_CTA_PAIR) ? 2 : 1;
+    p.num_sms = d.sms;
+    p.max_share = (flags & MOCO_NCE_SHARE4) ? 4 : ((flags & MOCO_NCE_SHARE2) ? 2 : 1);
+    p.slices = 0; p.n_pad = 0;
+    e = launch_nce_tc(p, ws, stream);
+    if (e != cudaSuccess) return cuda_fail("tcgen05 stats kernel", e);
+    e = launch_combine_partial(N, p.slices, p.n_pad, static_cast<float2*>(ms_out), ws, stream);
+    if (e != cudaSuccess) return cuda_fail("combine kernel", e);
+    return MOCO_OK;
+}
+
+int moco_nce_shard_merge(const void* ms_all, int world, int N, int C, float inv_T, float* lse, float* loss_rows,
+                         float* prob_rows, float* loss_prob, void* workspace, size_t workspace_bytes, void* stream_) {
+    g_err[0] = 0;
+    if (!ms_all || !lse || !loss_rows || !prob_rows || !loss_prob || !workspace || world < 1 || world > kMaxCtas || N <= 0) {
+        set_error("moco_nce_shard_merge: bad argument");
+        return MOCO_ERR_INVALID;
+    }
+    NceWorkspace ws = carve_workspace(workspace, N, C);
+    if (workspace_bytes < ws.bytes) { set_error("moco_nce_shard_merge: workspace too small"); return MOCO_ERR_WORKSPACE; }
+    cudaError_t e = launch_combine_merge(N, world, inv_T, static_cast<const float2*>(ms_all), lse, loss_rows, prob_rows,
+                                         loss_prob, ws, static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return cuda_fail("combine kernel", e);
+    return MOCO_OK;
+}
+
+int moco_nce_shard_dq(const void* q_all, int q_dtype, const void* shard_bf16, const float* lse_all, int N, int C,
+                      int Ks, float inv_T, float* o_partial, void* workspace, size_t workspace_bytes, int flags,
+                      void* stream_) {
+    g_err[0] = 0;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NceWorkspace ws; DevInfo d;
+    int rc = shard_common("moco_nce_shard_dq", q_all, N, C, Ks, workspace, workspace_bytes, &ws, &d);
+    if (rc != MOCO_OK) return rc;
+    if (!shard_bf16 || !lse_all || !o_partial) { set_error("moco_nce_shard_dq: null pointer"); return MOCO_ERR_INVALID; }
+    // q_bf16 in the workspace was produced by moco_nce_shard_stats on the same workspace (fp32 inputs)
+    const __nv_bfloat16* qb = q_dtype == MOCO_BF16 ? static_cast<const __nv_bfloat16*>(q_all) : ws.q_bf16;
+    const int max_share = (flags & MOCO_NCE_SHARE4) ? 4 : ((flags & MOCO_NCE_SHARE2) ? 2 : 1);
+    int slices = 0, n_pad = 0;
+    cudaError_t e;
+    if (flags & MOCO_NCE_DQ_V2)
+        e = launch_nce_dq2_tc(qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, lse_all, d.sms, max_share, &slices, &n_pad, ws, stream);
+    else
+        e = launch_nce_dq_tc(qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, lse_all, d.sms, max_share, &slices, &n_pad, ws, stream);
+    if (e != cudaSuccess) return cuda_fail("tcgen05 dq kernel", e);
+    e = launch_dq_reduce(N, C, slices, n_pad, inv_T, nullptr, 0, nullptr, o_partial, ws.part_o, stream);
+    if (e != cudaSuccess) return cuda_fail("dq reduce kernel", e);
+    return MOCO_OK;
+}
+
+int moco_nce_shard_dq_finish(const float* o_own, const void* k_own, int k_dtype, const float* prob_rows_own, int N,
+                             int C, float inv_T, float* dq, void* stream_) {
+    g_err[0] = 0;
+    if (!o_own || !k_own || !prob_rows_own || !dq || N <= 0 || C <= 0) {
+        set_error("moco_nce_shard_dq_finish: bad argument");
+        return MOCO_ERR_INVALID;
+    }
+    cudaError_t e = launch_dq_reduce(N, C, 1, N, inv_T, k_own, k_dtype, prob_rows_own, dq, o_own,
+                                     static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return cuda_fail("dq finish kernel", e);
     return MOCO_OK;
 }
 

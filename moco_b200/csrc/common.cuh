@@ -48,11 +48,16 @@ cudaError_t launch_combine(int N, int C, int slices, int n_pad, float inv_T, flo
                            float* lse, float* loss_rows, float* prob_rows, float* loss_prob,
                            const NceWorkspace& ws, cudaStream_t stream);
 cudaError_t launch_dq_reduce(int N, int C, int slices, int n_pad, float inv_T, const void* k, int k_dtype,
-                             const float* prob_rows, float* dq, const NceWorkspace& ws, cudaStream_t stream);
+                             const float* prob_rows, float* dq, const float* part_o, cudaStream_t stream);
+cudaError_t launch_combine_partial(int N, int slices, int n_pad, float2* ms_out, const NceWorkspace& ws,
+                                   cudaStream_t stream);
+cudaError_t launch_combine_merge(int N, int world, float inv_T, const float2* ms_all, float* lse, float* loss_rows,
+                                 float* prob_rows, float* loss_prob, const NceWorkspace& ws, cudaStream_t stream);
 cudaError_t launch_bwd_dense(const float* g, const void* k, int k_dtype, const __nv_bfloat16* queue,
                              int N, int C, int K, float inv_T, float* dq, cudaStream_t stream);
 cudaError_t launch_enqueue(__nv_bfloat16* queue_bf16, float* queue_f32, const void* k_all, int k_dtype,
-                           int n_all, int C, int64_t K, int64_t index, cudaStream_t stream);
+                           int n_all, int C, int64_t K, int64_t index, int64_t shard_row0, int64_t shard_rows,
+                           cudaStream_t stream);
 cudaError_t launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t stream);
 cudaError_t launch_gather(const void* const* peers, int world, int rows_per_rank, const int64_t* src_rows,
                           int n_rows, size_t row_bytes, void* dst, int flags, cudaStream_t stream);

@@ -55,6 +55,7 @@ __device__ void finish_mean(unsigned int* counter, int N, const float* loss_rows
         for (int i = 0; i < nw; ++i) { sa += s_red[0][i]; sb += s_red[1][i]; }
         loss_prob[0] = sa / (float)N;
         loss_prob[1] = sb / (float)N;
+        *counter = 0u;          // re-arm for the next launch on this workspace
     }
 }
 
@@ -98,9 +99,26 @@ __global__ void combine_kernel(int N, int C, int K, int slices, int n_pad, float
                                float* __restrict__ logits,
                                float* __restrict__ lse, float* __restrict__ loss_rows,
                                float* __restrict__ prob_rows, float* __restrict__ loss_prob,
-                               unsigned int* __restrict__ counters) {
+                               unsigned int* __restrict__ counters, float2* __restrict__ ms_out) {
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp per q row
     const float scale2 = inv_T * kLog2e;
+    if (ms_out != nullptr) {
+        // partial mode (sharded queue): merge this rank's slices only -> one (max, sum) per row, no positive
+        if (i < N) {
+            int lane = threadIdx.x & 31;
+            float m = -INFINITY;
+            for (int s = lane; s < slices; s += 32) m = fmaxf(m, part_ms[(size_t)s * n_pad + i].x);
+            m = warp_max(m);
+            float l = 0.f;
+            for (int s = lane; s < slices; s += 32) {
+                float2 ms = part_ms[(size_t)s * n_pad + i];
+                if (ms.x != -INFINITY) l += ms.y * ex2(ms.x - m);
+            }
+            l = warp_sum(l);
+            if (lane == 0) ms_out[i] = make_float2(m, l);
+        }
+        return;
+    }
     if (i < N) {
         const float x0 = lpos[i] * scale2;         // positive logit, log2 domain
         int lane = threadIdx.x & 31;
@@ -133,7 +151,26 @@ cudaError_t launch_combine(int N, int C, int slices, int n_pad, float inv_T, flo
                            cudaStream_t stream) {
     const int rows_per_block = 8;
     combine_kernel<<<(N + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, stream>>>(
-        N, C, K, slices, n_pad, inv_T, ws.lpos, ws.part_ms, logits, lse, loss_rows, prob_rows, loss_prob, ws.counters);
+        N, C, K, slices, n_pad, inv_T, ws.lpos, ws.part_ms, logits, lse, loss_rows, prob_rows, loss_prob, ws.counters,
+        nullptr);
+    return cudaGetLastError();
+}
+
+// sharded queue, step 1: this rank's slices -> ms_out[N]
+cudaError_t launch_combine_partial(int N, int slices, int n_pad, float2* ms_out, const NceWorkspace& ws,
+                                   cudaStream_t stream) {
+    const int rows_per_block = 8;
+    combine_kernel<<<(N + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, stream>>>(
+        N, 0, 0, slices, n_pad, 1.f, nullptr, ws.part_ms, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ms_out);
+    return cudaGetLastError();
+}
+
+// sharded queue, step 2: merge the W ranks' (max, sum) [W, N] with the positive logit (ws.lpos) -> lse, loss, prob
+cudaError_t launch_combine_merge(int N, int world, float inv_T, const float2* ms_all, float* lse, float* loss_rows,
+                                 float* prob_rows, float* loss_prob, const NceWorkspace& ws, cudaStream_t stream) {
+    const int rows_per_block = 8;
+    combine_kernel<<<(N + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, stream>>>(
+        N, 0, 0, world, N, inv_T, ws.lpos, ms_all, nullptr, lse, loss_rows, prob_rows, loss_prob, ws.counters, nullptr);
     return cudaGetLastError();
 }
 
@@ -162,9 +199,13 @@ __global__ void dq_reduce_kernel(int N, int C, int slices, int n_pad, float inv_
             float4 v = s_part[g * lanes + lane];
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
+        const size_t base = (size_t)i * C + lane * 4;
+        if (prob_rows == nullptr) {          // raw mode (sharded queue): just the slice sum
+            *reinterpret_cast<float4*>(dq + base) = acc;
+            return;
+        }
         const float gscale = inv_T / (float)N;
         const float pm1 = prob_rows[i] - 1.f;
-        const size_t base = (size_t)i * C + lane * 4;
         float4 o;
         o.x = gscale * (acc.x + pm1 * load_as_float(k, k_dtype, base + 0));
         o.y = gscale * (acc.y + pm1 * load_as_float(k, k_dtype, base + 1));
@@ -175,9 +216,9 @@ __global__ void dq_reduce_kernel(int N, int C, int slices, int n_pad, float inv_
 }
 
 cudaError_t launch_dq_reduce(int N, int C, int slices, int n_pad, float inv_T, const void* k, int k_dtype,
-                             const float* prob_rows, float* dq, const NceWorkspace& ws, cudaStream_t stream) {
+                             const float* prob_rows, float* dq, const float* part_o, cudaStream_t stream) {
     if ((C & 3) != 0 || C > 1024) return cudaErrorNotSupported;
-    dq_reduce_kernel<<<N, 256, 0, stream>>>(N, C, slices, n_pad, inv_T, k, k_dtype, ws.part_o, prob_rows, dq);
+    dq_reduce_kernel<<<N, 256, 0, stream>>>(N, C, slices, n_pad, inv_T, k, k_dtype, part_o, prob_rows, dq);
     return cudaGetLastError();
 }
 

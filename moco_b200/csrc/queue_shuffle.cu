@@ -12,13 +12,14 @@ namespace moco {
 // ---------------------------------------------------------------------------
 __global__ void enqueue_kernel(__nv_bfloat16* __restrict__ qb, float* __restrict__ qf,
                                const void* __restrict__ k_all, int k_dtype, int n_all, int C, long long K,
-                               long long index) {
+                               long long index, long long row0, long long nrows) {
     const int vec_per_row = C >> 3;
     const long long total = (long long)n_all * vec_per_row;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
         int i = (int)(t / vec_per_row), v = (int)(t % vec_per_row);
-        long long dst = (index + i) % K;
+        long long dst = (index + i) % K - row0;       // ring slot, relative to the rows this buffer holds
+        if (dst < 0 || dst >= nrows) continue;
         float f[8];
         if (k_dtype == 0) {
             const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(k_all) + (size_t)i * C) + v * 2;
@@ -46,12 +47,13 @@ __global__ void enqueue_kernel(__nv_bfloat16* __restrict__ qb, float* __restrict
 // scalar variant for C % 8 != 0
 __global__ void enqueue_scalar_kernel(__nv_bfloat16* __restrict__ qb, float* __restrict__ qf,
                                       const void* __restrict__ k_all, int k_dtype, int n_all, int C, long long K,
-                                      long long index) {
+                                      long long index, long long row0, long long nrows) {
     const long long total = (long long)n_all * C;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
         int i = (int)(t / C), c = (int)(t % C);
-        long long dst = (index + i) % K;
+        long long dst = (index + i) % K - row0;
+        if (dst < 0 || dst >= nrows) continue;
         float f = k_dtype == 0 ? static_cast<const float*>(k_all)[t]
                                : __bfloat162float(static_cast<const __nv_bfloat16*>(k_all)[t]);
         qb[(size_t)dst * C + c] = __float2bfloat16_rn(f);
@@ -60,18 +62,18 @@ __global__ void enqueue_scalar_kernel(__nv_bfloat16* __restrict__ qb, float* __r
 }
 
 cudaError_t launch_enqueue(__nv_bfloat16* queue_bf16, float* queue_f32, const void* k_all, int k_dtype, int n_all,
-                           int C, int64_t K, int64_t index, cudaStream_t stream) {
+                           int C, int64_t K, int64_t index, int64_t row0, int64_t nrows, cudaStream_t stream) {
     if (n_all == 0) return cudaSuccess;
     if ((C & 7) == 0) {
         long long total = (long long)n_all * (C >> 3);
         int blocks = (int)((total + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        enqueue_kernel<<<blocks, 256, 0, stream>>>(queue_bf16, queue_f32, k_all, k_dtype, n_all, C, K, index);
+        enqueue_kernel<<<blocks, 256, 0, stream>>>(queue_bf16, queue_f32, k_all, k_dtype, n_all, C, K, index, row0, nrows);
     } else {
         long long total = (long long)n_all * C;
         int blocks = (int)((total + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        enqueue_scalar_kernel<<<blocks, 256, 0, stream>>>(queue_bf16, queue_f32, k_all, k_dtype, n_all, C, K, index);
+        enqueue_scalar_kernel<<<blocks, 256, 0, stream>>>(queue_bf16, queue_f32, k_all, k_dtype, n_all, C, K, index, row0, nrows);
     }
     return cudaGetLastError();
 }

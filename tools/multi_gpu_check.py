@@ -50,6 +50,36 @@ def main():
     res["dist_collect"] = bool(ok)
     res["ok"] = res["ok"] and bool(ok)
 
+    # ---- sharded queue (BASELINE configs[3]): loss / prob / dq / ring contents vs the replicated oracle
+    from moco_b200.NCE import ShardedMemoryMoCo
+    Ns, C, K, T = 64, 128, 4096 * world, 0.07
+    rng = np.random.default_rng(77)
+    unit = lambda n: O.bf16_round(O.l2_normalize(rng.standard_normal((n, C)).astype(np.float32)))
+    memory0 = unit(K)
+    smod = ShardedMemoryMoCo(C, K, T)
+    smod.memory.copy_(torch.from_numpy(memory0[smod.shard_row0:smod.shard_row0 + smod.shard_rows]))
+    smod = smod.to(dev)
+    orc = O.MemoryMoCoOracle(memory0, T)
+    ok_s = True
+    for step in range(3):
+        q_all, k_all = unit(Ns * world), unit(Ns * world)          # every rank draws the same global batch
+        own = slice(rank * Ns, (rank + 1) * Ns)
+        pre = orc.memory.copy()
+        out = orc.logits(q_all[own], k_all[own])
+        ref_loss, ref_prob = O.nce_softmax_loss(out), O.prob_metric(out)
+        ref_dq = O.nce_backward_dq(q_all[own], k_all[own], pre, T)
+        orc.enqueue(k_all)
+        qt = torch.from_numpy(q_all[own]).to(dev).requires_grad_(True)
+        loss, prob = smod.forward_loss(qt, torch.from_numpy(k_all[own]).to(dev), torch.from_numpy(k_all).to(dev))
+        loss.backward()
+        e_l, e_p = abs(float(loss) - ref_loss), abs(float(prob) - ref_prob) / ref_prob
+        e_dq = float(np.abs(qt.grad.cpu().numpy() - ref_dq).max() / np.abs(ref_dq).max())
+        ok_s = ok_s and e_l < 2e-4 and e_p < 1e-3 and e_dq < 5e-3 and smod.index == orc.index
+        res[f"sharded_step{step}"] = [e_l, e_p, e_dq]
+    ok_s = ok_s and np.array_equal(smod.full_memory().cpu().numpy(), orc.memory)
+    res["sharded_queue"] = bool(ok_s)
+    res["ok"] = res["ok"] and bool(ok_s)
+
     # ---- bandwidth: BASELINE batch (256 x 3 x 224 x 224), fp32 and bf16, bulk-async vs LDG kernels
     ctx = ShuffleContext.get()
     n = 256
