@@ -97,6 +97,9 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype,
  * kernel; MOCO_PROF_DQ: the dq kernel).  Pass NULLs to clear.  Not thread-safe. */
 enum { MOCO_PROF_STATS = 1, MOCO_PROF_DQ = 2 };
 int moco_prof_set_events(int kernel, void* ev_start, void* ev_stop);
+/* Bring-up only: with env MOCO_DEBUG_MODE & 8 the stats kernel leaves per-CTA wait-cycle counters in the
+ * workspace; this copies `n_words` 64-bit words of them to the host (synchronous). */
+int moco_debug_read_prof(void* workspace, int N, int C, unsigned long long* out_host, int n_words);
 
 /* Backward of the dense-logits compatibility API (MemoryMoCo.forward returning
  * `out`, then an arbitrary upstream gradient):

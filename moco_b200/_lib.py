@@ -26,6 +26,7 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_size_t, c_int, c_void_p]),
     "moco_prof_set_events": (c_int, [c_int, c_void_p, c_void_p]),
+    "moco_debug_read_prof": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int]),
     "moco_nce_bwd_dense": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
                                    c_void_p, c_void_p]),
     "moco_queue_enqueue": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_void_p]),

@@ -148,6 +148,12 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
     return MOCO_OK;
 }
 
+int moco_debug_read_prof(void* workspace, int N, int C, unsigned long long* out_host, int n_words) {
+    NceWorkspace ws = carve_workspace(workspace, N, C);
+    cudaError_t e = cudaMemcpy(out_host, ws.part_o, sizeof(unsigned long long) * (size_t)n_words, cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? MOCO_OK : MOCO_ERR_CUDA;
+}
+
 int moco_prof_set_events(int kernel, void* ev_start, void* ev_stop) {
     g_err[0] = 0;
     if (kernel < 0 || kernel > 2) { set_error("moco_prof_set_events: bad kernel id"); return MOCO_ERR_INVALID; }

@@ -39,6 +39,7 @@ struct StatsArgs {
     float* logits;        // optional [N, K+1]
     float2* part_ms;      // [slices, n_pad]
     int debug;            // bring-up only (env MOCO_DEBUG_MODE): 1 = no epilogue math, 2 = no MMA issue, 4 = no TMA
+    unsigned long long* prof;   // bring-up only (MOCO_DEBUG_MODE & 8): per-CTA wait-cycle counters [8]
 };
 
 // G  = tcgen05 cta_group (1: M = 128 per CTA; 2: M = 256 per CTA pair, B tile split across the pair)
@@ -108,12 +109,13 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 else        tma_load_2d(&tm_q, qfull, q_s + kc * kSlab, kc * 64, row0);
             }
             int it = 0;
+            long long prof_empty = 0;
             for (int t = t0; t < t1; ++t) {
                 const int brow = t * kStatsBN + (int)rank * (kStatsBN / G);
                 for (int kc = 0; kc < kchunks; ++kc, ++it) {
                     const int st = it % NS;
                     const uint32_t ph = (uint32_t)(it / NS) & 1u;
-                    mbar_wait(&empty[st], ph ^ 1u);
+                    { long long c0 = clock64(); mbar_wait(&empty[st], ph ^ 1u); prof_empty += clock64() - c0; }
                     if (a.debug & 4) { if (rank == 0) mbar_arrive(&full[st]); continue; }
                     if (rank == 0) mbar_arrive_expect_tx(&full[st], (uint32_t)(kStageBytes * G));
                     if (G == 2) {
@@ -128,6 +130,7 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     }
                 }
             }
+            if (a.prof) a.prof[blockIdx.x * 8 + 2] = (unsigned long long)prof_empty;
         }
     } else if (warp == 1) {
         if (lane == 0 && rank == 0) {
@@ -136,16 +139,17 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             mbar_wait(qfull, 0);
             tc_fence_after();
             int it = 0, lt = 0;
+            long long prof_tempty = 0, prof_full = 0, prof_t0 = clock64();
             for (int t = t0; t < t1; ++t, ++lt) {
                 const int acc = lt & 1;
                 const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
-                mbar_wait(&tempty[acc], aph ^ 1u);
+                { long long c0 = clock64(); mbar_wait(&tempty[acc], aph ^ 1u); prof_tempty += clock64() - c0; }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kStatsBN);
                 for (int kc = 0; kc < kchunks; ++kc, ++it) {
                     const int st = it % NS;
                     const uint32_t ph = (uint32_t)(it / NS) & 1u;
-                    mbar_wait(&full[st], ph);
+                    { long long c0 = clock64(); mbar_wait(&full[st], ph); prof_full += clock64() - c0; }
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(q_s + kc * kSlab);
                     const uint32_t b_addr = smem_u32(b_s + (size_t)st * kStageBytes);
@@ -158,6 +162,11 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     if (CS > 1) umma_commit_mc(&empty[st], kMask); else umma_commit<G>(&empty[st]);
                 }
                 umma_commit<G>(&tfull[acc]);
+            }
+            if (a.prof) {
+                a.prof[blockIdx.x * 8 + 0] = (unsigned long long)prof_tempty;
+                a.prof[blockIdx.x * 8 + 1] = (unsigned long long)prof_full;
+                a.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - prof_t0);
             }
         }
     } else if (warp >= 4) {
@@ -215,10 +224,11 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             }
         };
         int lt = 0;
+        long long prof_tfull = 0, prof_e0 = clock64();
         for (int t = t0; t < t1; ++t, ++lt) {
             const int acc = lt & 1;
             const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
-            mbar_wait(&tfull[acc], aph);
+            { long long c0 = clock64(); mbar_wait(&tfull[acc], aph); prof_tfull += clock64() - c0; }
             tc_fence_after();
             const int col = cgrp * kEpiCols;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kStatsBN + col);
@@ -238,6 +248,10 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 }
                 if (!(a.debug & 1)) fold(r, t * kStatsBN + col + ch * 32);
             }
+        }
+        if (a.prof && warp == 4 && lane == 0) {
+            a.prof[blockIdx.x * 8 + 3] = (unsigned long long)prof_tfull;
+            a.prof[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - prof_e0);
         }
         // combine the column groups of each row (fixed order), then publish the slice partial
         if (cgrp > 0) red_s[(cgrp - 1) * kRowsPerCta + row_local] = make_float2(m, s);
@@ -508,6 +522,7 @@ cudaError_t launch_nce_tc(NceTcParams& p, const NceWorkspace& ws, cudaStream_t s
     a.logits = p.logits;
     a.part_ms = ws.part_ms;
     a.debug = debug_mode();
+    a.prof = (a.debug & 8) ? reinterpret_cast<unsigned long long*>(ws.part_o) : nullptr;
     auto fill = [](StatsArgs& x, int slices) { x.slices = slices; };
     static KernelCache kc[4];
     const int mgroups = mblks / CS, per_slice = mblks * G;

@@ -277,6 +277,60 @@ def test_shufflebn_full_size_images_roundtrip(dtype):
     assert torch.equal(back, x)
 
 
+def test_sharded_queue_world1_matches_oracle():
+    """ShardedMemoryMoCo at world_size 1 (one shard == the whole ring): same loss / prob / dq / FIFO as the
+    reference's replicated MemoryMoCo.  (world_size > 1: tests/test_gpu_multi.py.)"""
+    from moco_b200.NCE import ShardedMemoryMoCo
+    rng = np.random.default_rng(11)
+    N, C, K, T = 64, 128, 4096, 0.07
+    mem = rand_unit(rng, K, C)
+    mod = ShardedMemoryMoCo(C, K, T)
+    mod.memory.copy_(torch.from_numpy(mem))
+    mod = mod.cuda()
+    orc = O.MemoryMoCoOracle(mem, T)
+    for _ in range(3):
+        q, k = rand_unit(rng, N, C), rand_unit(rng, N, C)
+        pre = orc.memory.copy()
+        out = orc.logits(q, k)
+        dq = O.nce_backward_dq(q, k, pre, T)
+        orc.enqueue(k)
+        qt = torch.from_numpy(q).cuda().requires_grad_(True)
+        loss, prob = mod.forward_loss(qt, torch.from_numpy(k).cuda(), torch.from_numpy(k).cuda())
+        loss.backward()
+        assert abs(float(loss) - O.nce_softmax_loss(out)) < 2e-4
+        assert abs(float(prob) - O.prob_metric(out)) < 1e-3 * O.prob_metric(out)
+        assert np.abs(qt.grad.cpu().numpy() - dq).max() / np.abs(dq).max() < 5e-3
+        assert mod.index == orc.index
+    np.testing.assert_array_equal(mod.full_memory().cpu().numpy(), orc.memory)
+
+
+@pytest.mark.parametrize("W", [2, 8])
+def test_enqueue_shard_windows_reassemble_the_ring(W):
+    """moco_queue_enqueue_shard on W disjoint row windows == the reference's index_copy_ on the full ring
+    (ring slot g -> rank g // (K/W), local row g % (K/W)); bit-exact incl. a wrap across the last/first shard."""
+    from moco_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(W)
+    K, C, n_all = 1024, 64, 96
+    rows = K // W
+    mem = rng.standard_normal((K, C)).astype(np.float32)
+    orc = O.MemoryMoCoOracle(mem, 0.07, index=K - 40)
+    shards_f = [torch.from_numpy(mem[r * rows:(r + 1) * rows].copy()).cuda() for r in range(W)]
+    shards_b = [s.bfloat16() for s in shards_f]
+    index = K - 40
+    for _ in range(3):
+        k_all = rng.standard_normal((n_all, C)).astype(np.float32)
+        orc.enqueue(k_all)
+        kt = torch.from_numpy(k_all).cuda()
+        for r in range(W):
+            rc = lib.moco_queue_enqueue_shard(shards_b[r].data_ptr(), shards_f[r].data_ptr(), kt.data_ptr(), 0, n_all, C,
+                                              K, index, r * rows, rows, torch.cuda.current_stream().cuda_stream)
+            assert rc == 0
+        index = (index + n_all) % K
+    np.testing.assert_array_equal(torch.cat(shards_f).cpu().numpy(), orc.memory)
+    np.testing.assert_array_equal(torch.cat(shards_b).float().cpu().numpy(), O.bf16_round(orc.memory))
+
+
 def test_cpu_tensors_fail_loudly():
     from moco_b200.NCE import MemoryMoCo
     mod = MemoryMoCo(64, 32, 0.07)          # never moved to CUDA
