@@ -39,16 +39,18 @@ enum {
 
 enum { MOCO_F32 = 0, MOCO_BF16 = 1 };
 
-/* moco_nce_fwd `flags` */
+/* moco_nce_fwd `flags` (0 = the tuned defaults; the rest select measured alternatives, see profiles/) */
 enum {
-    MOCO_NCE_AUTO = 0,         /* tcgen05 kernel when the shape allows it (C % 64 == 0, C <= 256) */
-    MOCO_NCE_FORCE_SIMT = 1,   /* generic CUDA-core kernel (any shape)                             */
-    MOCO_NCE_CTA_PAIR = 2,     /* tcgen05.mma.cta_group::2 (M = 256 per CTA pair)                  */
-    MOCO_NCE_SINGLE_CTA = 4,   /* tcgen05.mma.cta_group::1 (M = 128 per CTA)                       */
-    MOCO_NCE_SHARE2 = 8,       /* share queue tiles across 2-CTA clusters by TMA multicast (halves */
-                               /* L2->SM traffic; measured time-neutral on B200, so off by default) */
-    MOCO_NCE_SHARE4 = 16,      /* same with 4-CTA clusters                                          */
-    MOCO_NCE_DQ_V2 = 32        /* dq pass with q and P as TMEM-resident A operands                 */
+    MOCO_NCE_AUTO = 0,         /* tcgen05 kernels when the shape allows it (C % 64 == 0, C <= 256)   */
+    MOCO_NCE_FORCE_SIMT = 1,   /* generic CUDA-core kernel (any shape)                               */
+    MOCO_NCE_CTA_PAIR = 2,     /* statistics kernel on tcgen05.mma.cta_group::2 (M = 256 per pair)   */
+    MOCO_NCE_SINGLE_CTA = 4,   /* require the tcgen05 path (error instead of the generic fallback)   */
+    MOCO_NCE_SHARE2 = 8,       /* share queue tiles across 2-CTA clusters by TMA multicast (halves   */
+                               /* L2 reads; measured time-neutral on B200, so off by default)         */
+    MOCO_NCE_SHARE4 = 16,      /* same with 4-CTA clusters                                            */
+    MOCO_NCE_DQ_V1 = 32,       /* first-generation dq kernel (P through shared memory)                */
+    MOCO_NCE_STATS_TS = 64,    /* statistics kernel with the q block in TMEM (192-row tiles)          */
+    MOCO_NCE_EPI8 = 128        /* 8 epilogue warps instead of two ping-pong groups of 8               */
 };
 
 int moco_abi_version(void);

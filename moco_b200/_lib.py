@@ -13,7 +13,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_uint3
 from . import build as _build
 
 MOCO_F32, MOCO_BF16 = 0, 1
-NCE_AUTO, NCE_FORCE_SIMT, NCE_CTA_PAIR, NCE_SINGLE_CTA, NCE_SHARE2, NCE_SHARE4, NCE_DQ_V2 = 0, 1, 2, 4, 8, 16, 32
+NCE_AUTO, NCE_FORCE_SIMT, NCE_CTA_PAIR, NCE_SINGLE_CTA, NCE_SHARE2, NCE_SHARE4, NCE_DQ_V1, NCE_STATS_TS, NCE_EPI8 = 0, 1, 2, 4, 8, 16, 32, 64, 128
 GATHER_AUTO, GATHER_LDG = 0, 1
 
 # every symbol include/moco_b200.h declares: name -> (restype, argtypes)

@@ -118,9 +118,10 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
         p.num_sms = d.sms;
         const int max_share = (flags & MOCO_NCE_SHARE4) ? 4 : ((flags & MOCO_NCE_SHARE2) ? 2 : 1);
         p.max_share = max_share;
+        p.epi_warps = (flags & MOCO_NCE_EPI8) ? 8 : 16;
         p.slices = 0; p.n_pad = 0;
         prof_mark(MOCO_PROF_STATS, 0, stream);
-        e = launch_nce_tc(p, ws, stream);
+        e = (flags & MOCO_NCE_STATS_TS) ? launch_nce_stats3(p, p.epi_warps, ws, stream) : launch_nce_tc(p, ws, stream);
         prof_mark(MOCO_PROF_STATS, 1, stream);
         if (e == cudaSuccess) {
             e = launch_combine(N, C, p.slices, p.n_pad, inv_T, logits, K, lse, loss_rows, prob_rows, loss_prob, ws, stream);
@@ -128,10 +129,10 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
             if (dq) {
                 int slices = 0, n_pad = 0;
                 prof_mark(MOCO_PROF_DQ, 0, stream);
-                if (flags & MOCO_NCE_DQ_V2)
-                    e = launch_nce_dq2_tc(qb, queue, N, C, K, inv_T, lse, d.sms, max_share, &slices, &n_pad, ws, stream);
-                else
+                if (flags & MOCO_NCE_DQ_V1)
                     e = launch_nce_dq_tc(qb, queue, N, C, K, inv_T, lse, d.sms, max_share, &slices, &n_pad, ws, stream);
+                else
+                    e = launch_nce_dq2_tc(qb, queue, N, C, K, inv_T, lse, d.sms, max_share, &slices, &n_pad, ws, stream);
                 prof_mark(MOCO_PROF_DQ, 1, stream);
                 if (e != cudaSuccess) return cuda_fail("tcgen05 dq kernel", e);
                 e = launch_dq_reduce(N, C, slices, n_pad, inv_T, k, qk_dtype, prob_rows, dq, ws.part_o, stream);
@@ -243,8 +244,9 @@ int moco_nce_shard_stats(const void* q_all, const void* k_all, int qk_dtype, con
     p.cta_group = (flags & MOCO_NCE_CTA_PAIR) ? 2 : 1;
     p.num_sms = d.sms;
     p.max_share = (flags & MOCO_NCE_SHARE4) ? 4 : ((flags & MOCO_NCE_SHARE2) ? 2 : 1);
+    p.epi_warps = (flags & MOCO_NCE_EPI8) ? 8 : 16;
     p.slices = 0; p.n_pad = 0;
-    e = launch_nce_tc(p, ws, stream);
+    e = (flags & MOCO_NCE_STATS_TS) ? launch_nce_stats3(p, p.epi_warps, ws, stream) : launch_nce_tc(p, ws, stream);
     if (e != cudaSuccess) return cuda_fail("tcgen05 stats kernel", e);
     e = launch_combine_partial(N, p.slices, p.n_pad, static_cast<float2*>(ms_out), ws, stream);
     if (e != cudaSuccess) return cuda_fail("combine kernel", e);
@@ -280,10 +282,10 @@ int moco_nce_shard_dq(const void* q_all, int q_dtype, const void* shard_bf16, co
     const int max_share = (flags & MOCO_NCE_SHARE4) ? 4 : ((flags & MOCO_NCE_SHARE2) ? 2 : 1);
     int slices = 0, n_pad = 0;
     cudaError_t e;
-    if (flags & MOCO_NCE_DQ_V2)
-        e = launch_nce_dq2_tc(qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, lse_all, d.sms, max_share, &slices, &n_pad, ws, stream);
-    else
+    if (flags & MOCO_NCE_DQ_V1)
         e = launch_nce_dq_tc(qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, lse_all, d.sms, max_share, &slices, &n_pad, ws, stream);
+    else
+        e = launch_nce_dq2_tc(qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, lse_all, d.sms, max_share, &slices, &n_pad, ws, stream);
     if (e != cudaSuccess) return cuda_fail("tcgen05 dq kernel", e);
     e = launch_dq_reduce(N, C, slices, n_pad, inv_T, nullptr, 0, nullptr, o_partial, ws.part_o, stream);
     if (e != cudaSuccess) return cuda_fail("dq reduce kernel", e);

@@ -73,11 +73,13 @@ struct NceTcParams {
     int cta_group;                 // 1 or 2
     int num_sms;
     int max_share;                 // upper bound on the TMA-multicast cluster size (1, 2 or 4)
+    int epi_warps;                 // 8 or 16 epilogue warps
     // outputs of the launch decision
     int slices;
     int n_pad;
 };
 cudaError_t launch_nce_tc(NceTcParams& p, const NceWorkspace& ws, cudaStream_t stream);
+cudaError_t launch_nce_stats3(NceTcParams& p, int epi_warps, const NceWorkspace& ws, cudaStream_t stream);
 cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* queue, int N, int C, int K,
                               float inv_T, const float* lse, int num_sms, int max_share, int* slices_out,
                               int* n_pad_out, const NceWorkspace& ws, cudaStream_t stream);

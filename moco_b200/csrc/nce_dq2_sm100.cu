@@ -89,9 +89,10 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             // ------------------------------------------------ TMA producer (queue tiles only)
-            for (int i = 0; i < ntiles; ++i) {
-                const int st = i % NS;
-                mbar_wait(&kv_empty[st], ((uint32_t)(i / NS) & 1u) ^ 1u);
+            int st = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < ntiles; ++i, st = (st + 1 == NS) ? 0 : st + 1, ph ^= (st == 0) ? 1u : 0u) {
+                mbar_wait(&kv_empty[st], ph ^ 1u);
                 if (a.debug & 4) { mbar_arrive(&kv_full[st]); continue; }
                 mbar_arrive_expect_tx(&kv_full[st], (uint32_t)tile_bytes);
                 for (int kc = 0; kc < kchunks; ++kc) {
@@ -113,35 +114,49 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
             const uint32_t idesc_o = make_idesc_bf16(128, (uint32_t)a.C, 0, 1);     // O += P . tile    (A: TMEM, B: MN-major)
             mbar_wait(q_ready, 0);
             tc_fence_after();
+            // lean single-thread loops: descriptors built once and advanced by adds, running stage / phase counters
+            const uint64_t vk_desc0 = make_sw128_desc(smem_u32(v_s), 0, 1024);          // tile as K-major B (S MMA)
+            const uint64_t vm_desc0 = make_sw128_desc(smem_u32(v_s), kSlab64, 1024);    // tile as MN-major B (PV MMA)
+            constexpr uint64_t kSlabUnits = (uint64_t)(kSlab64 >> 4);
+            const uint64_t tile_units = (uint64_t)(tile_bytes >> 4);
+            int s_st = 0; uint32_t s_ph = 0; uint64_t s_vdesc = vk_desc0;
+            int o_st = 0; uint64_t o_vdesc = vm_desc0;
             auto issue_s = [&](int i) {
-                const int st = i % NS, b = i & 1;
-                mbar_wait(&kv_full[st], (uint32_t)(i / NS) & 1u);
+                const uint32_t b = (uint32_t)i & 1u;
+                mbar_wait(&kv_full[s_st], s_ph);
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(v_s + (size_t)st * tile_bytes);
-                const int ksteps = a.C >> 4;
-                for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t d = tmem_base + kSCol + b * (uint32_t)kDq2BN;
+                uint32_t qa = tmem_base + kQCol;
+                uint64_t vd = s_vdesc;
+                for (int kc = 0; kc < kchunks; ++kc) {
                     if (a.debug & 2) break;
-                    umma_ts<1>(tmem_base + kSCol + (uint32_t)(b * kDq2BN), tmem_base + kQCol + (uint32_t)(ks * 8),
-                               make_sw128_desc(v_addr + (ks >> 2) * kSlab64 + (ks & 3) * 32, 0, 1024), idesc_s,
-                               (uint32_t)(ks != 0));
+                    umma_ts<1>(d, qa, vd, idesc_s, (uint32_t)(kc != 0));
+                    umma_ts<1>(d, qa + 8, vd + 2, idesc_s, 1u);
+                    umma_ts<1>(d, qa + 16, vd + 4, idesc_s, 1u);
+                    umma_ts<1>(d, qa + 24, vd + 6, idesc_s, 1u);
+                    qa += 32;
+                    vd += kSlabUnits;
                 }
                 umma_commit<1>(&s_full[b]);
+                s_vdesc += tile_units;
+                if (++s_st == NS) { s_st = 0; s_ph ^= 1u; s_vdesc = vk_desc0; }
             };
             if (ntiles > 0) issue_s(0);
             if (ntiles > 1) issue_s(1);
             for (int i = 0; i < ntiles; ++i) {
-                const int st = i % NS, b = i & 1;
-                mbar_wait(&p_full[b], (uint32_t)(i >> 1) & 1u);
+                const uint32_t b = (uint32_t)i & 1u;
+                mbar_wait(&p_full[b], ((uint32_t)i >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(v_s + (size_t)st * tile_bytes);
 #pragma unroll
                 for (int kk = 0; kk < kDq2BN / 16; ++kk) {
                     if (a.debug & 2) break;
                     // A = P[:, 16kk..16kk+16) : 8 packed TMEM columns;  B = tile rows [16kk, 16kk+16) x C (MN-major)
-                    umma_ts<1>(tmem_base + kOCol2, tmem_base + kSCol + (uint32_t)(b * kDq2BN + kk * 8),
-                               make_sw128_desc(v_addr + kk * 2048, kSlab64, 1024), idesc_o, (uint32_t)((i | kk) != 0));
+                    umma_ts<1>(tmem_base + kOCol2, tmem_base + kSCol + b * (uint32_t)kDq2BN + (uint32_t)(kk * 8),
+                               o_vdesc + (uint64_t)(kk * 128), idesc_o, (uint32_t)((i | kk) != 0));
                 }
-                if (CS > 1) umma_commit_mc(&kv_empty[st], kMask); else umma_commit<1>(&kv_empty[st]);
+                if (CS > 1) umma_commit_mc(&kv_empty[o_st], kMask); else umma_commit<1>(&kv_empty[o_st]);
+                o_vdesc += tile_units;
+                if (++o_st == NS) { o_st = 0; o_vdesc = vm_desc0; }
                 if (i + 2 < ntiles) issue_s(i + 2);      // overwrites buffer b: ordered after PV(i) by the pipe
             }
             umma_commit<1>(o_full);

@@ -24,13 +24,7 @@ namespace moco {
 // Kernel A: per-slice softmax statistics (and optional dense logits)
 // =====================================================================================
 constexpr int kStatsBN = 256;          // queue rows per tile (UMMA N)
-// Epilogue warps: 2 per SM sub-partition.  Measured on B200 (tools/pipe_probe.py): the accumulator drain
-// (tcgen05.ld, ~64 B/clk/SM) is the floor of the epilogue, not MUFU/issue latency -- 16 warps were slower
-// (68.9 us vs 63.8 us at N=512, C=256, K=262144) than 8.
-constexpr int kEpiWarps = 8;
-constexpr int kEpiCols = kStatsBN / (kEpiWarps / 4);   // accumulator columns per epilogue thread per tile
-constexpr int kEpiChunks = kEpiCols / 32;              // 32-column tcgen05.ld per thread per tile
-constexpr int kStatsThreads = 128 + kEpiWarps * 32;    // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4.. epilogue
+// warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4.. epilogue (EW = 8 or 16 epilogue warps)
 
 struct StatsArgs {
     int N, C, K;
@@ -45,13 +39,19 @@ struct StatsArgs {
 // G  = tcgen05 cta_group (1: M = 128 per CTA; 2: M = 256 per CTA pair, B tile split across the pair)
 // CS = CTAs per cluster that handle DIFFERENT q row blocks but the SAME queue tiles (G == 1 only): each
 //      loads 1/CS of every queue tile and TMA-multicasts it to all CS CTAs, dividing L2->SM traffic by CS.
-template <int G, int CS>
-__global__ void __launch_bounds__(kStatsThreads, 1)
+template <int G, int CS, int EW>
+__global__ void __launch_bounds__(128 + EW * 32, 1)
 nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_queue,
                  const StatsArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kStageBytes = (kStatsBN / G) * 128;
+    constexpr int kEpiWarps = EW;
+    // EW == 8 : one epilogue group, every tile.   EW == 16: two groups of 8 warps in ping-pong -- group p owns
+    // accumulator buffer p and drains the tiles of parity p, so the exps of tile t overlap the drain of t+1.
+    constexpr int kEpiCols = 128;                          // accumulator columns per epilogue thread per tile
+    constexpr int kEpiChunks = kEpiCols / 32;              // 32-column tcgen05.ld per thread per tile
+    constexpr int kTileStep = (EW == 16) ? 2 : 1;
     const int kchunks = a.C >> 6;
     const int NS = a.stages;
     uint8_t* q_s = smem;
@@ -86,7 +86,7 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CS); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kEpiWarps * G); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8 * G); }
         mbar_init(qfull, 1);
         fence_mbar_init();
     }
@@ -102,71 +102,68 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     if (warp == 0) {
         if (lane == 0) {
             // ------------------------------------------------ TMA producer
+            // NOTE (measured, tools/trace_probe.py): the producer and the MMA issuer are single threads whose
+            // scalar instruction stream runs at ~4-6 cycles per dependent instruction; a runtime `it % NS`,
+            // `it / NS` or a rebuilt 64-bit descriptor per stage costs hundreds of cycles -- more than the
+            // 512 tensor cycles a stage holds.  Everything in these loops is therefore strength-reduced to
+            // running counters and adds.
             const uint32_t qfull_addr = (G == 2) ? mapa_shared(smem_u32(qfull), 0) : smem_u32(qfull);
             if (rank == 0) mbar_arrive_expect_tx(qfull, (uint32_t)(kchunks * kSlab * G));
             for (int kc = 0; kc < kchunks; ++kc) {
                 if (G == 2) tma_load_2d_2sm(&tm_q, qfull_addr, q_s + kc * kSlab, kc * 64, row0);
                 else        tma_load_2d(&tm_q, qfull, q_s + kc * kSlab, kc * 64, row0);
             }
-            int it = 0;
-            long long prof_empty = 0;
-            for (int t = t0; t < t1; ++t) {
-                const int brow = t * kStatsBN + (int)rank * (kStatsBN / G);
-                for (int kc = 0; kc < kchunks; ++kc, ++it) {
-                    const int st = it % NS;
-                    const uint32_t ph = (uint32_t)(it / NS) & 1u;
-                    { long long c0 = clock64(); mbar_wait(&empty[st], ph ^ 1u); prof_empty += clock64() - c0; }
-                    if (a.debug & 4) { if (rank == 0) mbar_arrive(&full[st]); continue; }
+            int st = 0;
+            uint32_t ph = 0;
+            uint8_t* dst = b_s + ((CS > 1) ? (size_t)crank * (kStatsBN / CS) * 128 : 0);
+            const uint32_t full0 = (G == 2) ? mapa_shared(smem_u32(&full[0]), 0) : 0u;
+            int brow = t0 * kStatsBN + (int)rank * (kStatsBN / G) + ((CS > 1) ? (int)crank * (kStatsBN / CS) : 0);
+            for (int t = t0; t < t1; ++t, brow += kStatsBN) {
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&empty[st], ph ^ 1u);
                     if (rank == 0) mbar_arrive_expect_tx(&full[st], (uint32_t)(kStageBytes * G));
-                    if (G == 2) {
-                        tma_load_2d_2sm(&tm_queue, mapa_shared(smem_u32(&full[st]), 0), b_s + (size_t)st * kStageBytes, kc * 64, brow);
-                    } else if (CS > 1) {
-                        // this CTA's 1/CS of the tile rows, multicast into every CTA of the cluster
-                        constexpr int kPart = kStatsBN / CS;
-                        tma_load_2d_mc(&tm_queue, &full[st], b_s + (size_t)st * kStageBytes + (size_t)crank * kPart * 128,
-                                       kc * 64, brow + (int)crank * kPart, kMask);
-                    } else {
-                        tma_load_2d(&tm_queue, &full[st], b_s + (size_t)st * kStageBytes, kc * 64, brow);
-                    }
+                    if (G == 2)      tma_load_2d_2sm(&tm_queue, full0 + (uint32_t)st * 8u, dst, kc * 64, brow);
+                    else if (CS > 1) tma_load_2d_mc(&tm_queue, &full[st], dst, kc * 64, brow, kMask);
+                    else             tma_load_2d(&tm_queue, &full[st], dst, kc * 64, brow);
+                    dst += kStageBytes;
+                    if (++st == NS) { st = 0; ph ^= 1u; dst -= (size_t)NS * kStageBytes; }
                 }
             }
-            if (a.prof) a.prof[blockIdx.x * 8 + 2] = (unsigned long long)prof_empty;
         }
     } else if (warp == 1) {
         if (lane == 0 && rank == 0) {
             // ------------------------------------------------ MMA issuer (pair leader only)
             const uint32_t idesc = make_idesc_bf16(128 * G, kStatsBN, 0, 0);
+            // descriptors differ from tile to tile only in the 14-bit start-address field: build once, then add
+            const uint64_t a_desc0 = make_sw128_desc(smem_u32(q_s), 0, 1024);
+            const uint64_t b_desc0 = make_sw128_desc(smem_u32(b_s), 0, 1024);
+            constexpr uint64_t kStageUnits = (uint64_t)(kStageBytes >> 4), kSlabUnits = (uint64_t)(kSlab >> 4);
             mbar_wait(qfull, 0);
             tc_fence_after();
-            int it = 0, lt = 0;
-            long long prof_tempty = 0, prof_full = 0, prof_t0 = clock64();
-            for (int t = t0; t < t1; ++t, ++lt) {
-                const int acc = lt & 1;
-                const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
-                { long long c0 = clock64(); mbar_wait(&tempty[acc], aph ^ 1u); prof_tempty += clock64() - c0; }
+            int st = 0;
+            uint32_t ph = 0;
+            uint64_t b_desc = b_desc0;
+            uint32_t acc = 0, aph = 0;
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&tempty[acc], aph ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kStatsBN);
-                for (int kc = 0; kc < kchunks; ++kc, ++it) {
-                    const int st = it % NS;
-                    const uint32_t ph = (uint32_t)(it / NS) & 1u;
-                    { long long c0 = clock64(); mbar_wait(&full[st], ph); prof_full += clock64() - c0; }
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)kStatsBN;
+                uint64_t a_desc = a_desc0;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&full[st], ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(q_s + kc * kSlab);
-                    const uint32_t b_addr = smem_u32(b_s + (size_t)st * kStageBytes);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (a.debug & 2) break;
-                        umma_ss<G>(d_tmem, make_sw128_desc(a_addr + k * 32, 0, 1024),
-                                   make_sw128_desc(b_addr + k * 32, 0, 1024), idesc, (uint32_t)((kc | k) != 0));
-                    }
+                    umma_ss<G>(d_tmem, a_desc, b_desc, idesc, (uint32_t)(kc != 0));
+                    umma_ss<G>(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+                    umma_ss<G>(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                    umma_ss<G>(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
                     if (CS > 1) umma_commit_mc(&empty[st], kMask); else umma_commit<G>(&empty[st]);
+                    a_desc += kSlabUnits;
+                    b_desc += kStageUnits;
+                    if (++st == NS) { st = 0; ph ^= 1u; b_desc = b_desc0; }
                 }
                 umma_commit<G>(&tfull[acc]);
-            }
-            if (a.prof) {
-                a.prof[blockIdx.x * 8 + 0] = (unsigned long long)prof_tempty;
-                a.prof[blockIdx.x * 8 + 1] = (unsigned long long)prof_full;
-                a.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - prof_t0);
+                acc ^= 1u;
+                aph ^= (acc == 0u) ? 1u : 0u;
             }
         }
     } else if (warp >= 4) {
@@ -223,30 +220,32 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 }
             }
         };
-        int lt = 0;
+        int lt = (EW == 16) ? (cgrp >> 1) : 0;
         long long prof_tfull = 0, prof_e0 = clock64();
-        for (int t = t0; t < t1; ++t, ++lt) {
+        for (int t = t0 + lt; t < t1; t += kTileStep, lt += kTileStep) {
             const int acc = lt & 1;
             const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
             { long long c0 = clock64(); mbar_wait(&tfull[acc], aph); prof_tfull += clock64() - c0; }
             tc_fence_after();
-            const int col = cgrp * kEpiCols;
+            const int col = (cgrp & 1) * kEpiCols;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kStatsBN + col);
+            {
 #pragma unroll 1
-            for (int ch = 0; ch < kEpiChunks; ++ch) {
-                uint32_t r[32];
-                tmem_ld32(taddr + (uint32_t)(ch * 32), r);
-                tmem_ld_wait();
-                if (ch == kEpiChunks - 1) {
-                    // the whole accumulator slice of this warp is in registers: hand the buffer back to the MMA
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (G == 2) mbar_arrive_cluster(&tempty[acc], 0);
-                        else        mbar_arrive(&tempty[acc]);
+                for (int ch = 0; ch < kEpiChunks; ++ch) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + (uint32_t)(ch * 32), r);
+                    tmem_ld_wait();
+                    if (ch == kEpiChunks - 1) {
+                        // the whole accumulator slice of this warp is in registers: hand the buffer back to the MMA
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (G == 2) mbar_arrive_cluster_relaxed(&tempty[acc], 0);
+                            else        mbar_arrive(&tempty[acc]);
+                        }
                     }
+                    if (!(a.debug & 1)) fold(r, t * kStatsBN + col + ch * 32);
                 }
-                if (!(a.debug & 1)) fold(r, t * kStatsBN + col + ch * 32);
             }
         }
         if (a.prof && warp == 4 && lane == 0) {
@@ -355,9 +354,9 @@ nce_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             // ------------------------------------------------ TMA producer
             mbar_arrive_expect_tx(qfull, (uint32_t)tile_bytes);
             for (int kc = 0; kc < kchunks; ++kc) tma_load_2d(&tm_q, qfull, q_s + kc * kSlab, kc * 64, row0);
-            for (int i = 0; i < ntiles; ++i) {
-                const int st = i % NS;
-                const uint32_t ph = (uint32_t)(i / NS) & 1u;
+            int st = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < ntiles; ++i, st = (st + 1 == NS) ? 0 : st + 1, ph ^= (st == 0) ? 1u : 0u) {
                 mbar_wait(&kv_empty[st], ph ^ 1u);
                 mbar_arrive_expect_tx(&kv_full[st], (uint32_t)tile_bytes);
                 for (int kc = 0; kc < kchunks; ++kc) {
@@ -380,43 +379,52 @@ nce_dq_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             const uint32_t idesc_o = make_idesc_bf16(128, (uint32_t)a.C, 0, 1);    // O += P . tile   (B MN-major)
             mbar_wait(qfull, 0);
             tc_fence_after();
+            // lean single-thread loops (see the note in nce_stats_kernel): descriptors are built once and
+            // advanced by adds, stage / phase are running counters
+            const uint64_t q_desc0 = make_sw128_desc(smem_u32(q_s), 0, 1024);
+            const uint64_t p_desc0 = make_sw128_desc(smem_u32(p_s), 0, 1024);
+            const uint64_t vk_desc0 = make_sw128_desc(smem_u32(v_s), 0, 1024);         // tile as K-major B (S MMA)
+            const uint64_t vm_desc0 = make_sw128_desc(smem_u32(v_s), kSlab, 1024);     // tile as MN-major B (PV MMA)
+            constexpr uint64_t kSlabUnits = (uint64_t)(kSlab >> 4);
+            const uint64_t tile_units = (uint64_t)(tile_bytes >> 4);
+            int s_st = 0; uint32_t s_ph = 0; uint64_t s_vdesc = vk_desc0;             // S side ring cursor
+            int o_st = 0; uint64_t o_vdesc = vm_desc0;                                 // PV side ring cursor
             auto issue_s = [&](int i) {
-                const int st = i % NS;
-                const int b = i & 1;
-                mbar_wait(&kv_full[st], (uint32_t)(i / NS) & 1u);
-                mbar_wait(&s_empty[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+                const uint32_t b = (uint32_t)i & 1u;
+                mbar_wait(&kv_full[s_st], s_ph);
+                mbar_wait(&s_empty[b], (((uint32_t)i >> 1) & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t q_addr = smem_u32(q_s), v_addr = smem_u32(v_s + (size_t)st * tile_bytes);
+                const uint32_t d = tmem_base + b * (uint32_t)kDqBN;
+                uint64_t qd = q_desc0, vd = s_vdesc;
                 for (int kc = 0; kc < kchunks; ++kc) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        umma_ss<1>(tmem_base + (uint32_t)(b * kDqBN),
-                                   make_sw128_desc(q_addr + kc * kSlab + k * 32, 0, 1024),
-                                   make_sw128_desc(v_addr + kc * kSlab + k * 32, 0, 1024), idesc_s,
-                                   (uint32_t)((kc | k) != 0));
-                    }
+                    umma_ss<1>(d, qd, vd, idesc_s, (uint32_t)(kc != 0));
+                    umma_ss<1>(d, qd + 2, vd + 2, idesc_s, 1u);
+                    umma_ss<1>(d, qd + 4, vd + 4, idesc_s, 1u);
+                    umma_ss<1>(d, qd + 6, vd + 6, idesc_s, 1u);
+                    qd += kSlabUnits;
+                    vd += kSlabUnits;
                 }
                 umma_commit<1>(&s_full[b]);
+                s_vdesc += tile_units;
+                if (++s_st == NS) { s_st = 0; s_ph ^= 1u; s_vdesc = vk_desc0; }
             };
             if (ntiles > 0) issue_s(0);
             for (int i = 0; i < ntiles; ++i) {
                 if (i + 1 < ntiles) issue_s(i + 1);
-                const int st = i % NS;
                 mbar_wait(p_full, (uint32_t)i & 1u);
                 tc_fence_after();
-                const uint32_t p_addr = smem_u32(p_s), v_addr = smem_u32(v_s + (size_t)st * tile_bytes);
+                // A = P[:, 16kk .. 16kk+16) (K-major slab kk/4, 32-byte step kk%4)
+                // B = tile rows [16kk, 16kk+16) x C (MN-major: 64-element chunks LBO = slab apart, 8-row groups
+                //     SBO = 1024 B apart): 2048 B (= 128 descriptor units) per 16 rows
 #pragma unroll
                 for (int kk = 0; kk < kDqBN / 16; ++kk) {
-                    // A = P[:, 16kk .. 16kk+16) (K-major slab kk/4, 32-byte step kk%4)
-                    // B = tile rows [16kk, 16kk+16) x C  (MN-major: 64-element chunks LBO = slab apart,
-                    //     8-row groups SBO = 1024 B apart)
-                    umma_ss<1>(tmem_base + kOCol,
-                               make_sw128_desc(p_addr + (kk >> 2) * kSlab + (kk & 3) * 32, 0, 1024),
-                               make_sw128_desc(v_addr + kk * 2048, kSlab, 1024), idesc_o,
-                               (uint32_t)((i | kk) != 0));
+                    umma_ss<1>(tmem_base + kOCol, p_desc0 + (uint64_t)((kk >> 2) * (kSlab >> 4) + (kk & 3) * 2),
+                               o_vdesc + (uint64_t)(kk * 128), idesc_o, (uint32_t)((i | kk) != 0));
                 }
-                if (CS > 1) umma_commit_mc(&kv_empty[st], kMask); else umma_commit<1>(&kv_empty[st]);
+                if (CS > 1) umma_commit_mc(&kv_empty[o_st], kMask); else umma_commit<1>(&kv_empty[o_st]);
                 umma_commit<1>(p_empty);
+                o_vdesc += tile_units;
+                if (++o_st == NS) { o_st = 0; o_vdesc = vm_desc0; }
             }
             umma_commit<1>(o_full);
         }
@@ -522,20 +530,27 @@ cudaError_t launch_nce_tc(NceTcParams& p, const NceWorkspace& ws, cudaStream_t s
     a.logits = p.logits;
     a.part_ms = ws.part_ms;
     a.debug = debug_mode();
-    a.prof = (a.debug & 8) ? reinterpret_cast<unsigned long long*>(ws.part_o) : nullptr;
+    a.prof = (a.debug & (8 | 16)) ? reinterpret_cast<unsigned long long*>(ws.part_o) : nullptr;
     auto fill = [](StatsArgs& x, int slices) { x.slices = slices; };
     static KernelCache kc[4];
     const int mgroups = mblks / CS, per_slice = mblks * G;
+    static KernelCache kc16[2];
+    if (G == 2 && p.epi_warps == 16)
+        return plan_and_launch(nce_stats_kernel<2, 1, 16>, kc16[0], 128 + 16 * 32, smem, 2, mgroups, per_slice, num_tiles,
+                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
     if (G == 2)
-        return plan_and_launch(nce_stats_kernel<2, 1>, kc[0], kStatsThreads, smem, 2, mgroups, per_slice, num_tiles,
+        return plan_and_launch(nce_stats_kernel<2, 1, 8>, kc[0], 128 + 8 * 32, smem, 2, mgroups, per_slice, num_tiles,
                                n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
     if (CS == 4)
-        return plan_and_launch(nce_stats_kernel<1, 4>, kc[1], kStatsThreads, smem, 4, mgroups, per_slice, num_tiles,
+        return plan_and_launch(nce_stats_kernel<1, 4, 8>, kc[1], 128 + 8 * 32, smem, 4, mgroups, per_slice, num_tiles,
                                n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
     if (CS == 2)
-        return plan_and_launch(nce_stats_kernel<1, 2>, kc[2], kStatsThreads, smem, 2, mgroups, per_slice, num_tiles,
+        return plan_and_launch(nce_stats_kernel<1, 2, 8>, kc[2], 128 + 8 * 32, smem, 2, mgroups, per_slice, num_tiles,
                                n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
-    return plan_and_launch(nce_stats_kernel<1, 1>, kc[3], kStatsThreads, smem, 1, mgroups, per_slice, num_tiles, n_pad,
+    if (p.epi_warps == 16)
+        return plan_and_launch(nce_stats_kernel<1, 1, 16>, kc16[1], 128 + 16 * 32, smem, 1, mgroups, per_slice, num_tiles,
+                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
+    return plan_and_launch(nce_stats_kernel<1, 1, 8>, kc[3], 128 + 8 * 32, smem, 1, mgroups, per_slice, num_tiles, n_pad,
                            &p.slices, stream, tm_q, tm_queue, a, fill);
 }
 

@@ -20,7 +20,11 @@ TIGHT = 2e-5               # what identical bf16 inputs + fp32 accumulation actu
 
 def _flags():
     from moco_b200 import _lib
-    return {"auto": _lib.NCE_AUTO, "simt": _lib.NCE_FORCE_SIMT, "tc1": _lib.NCE_SINGLE_CTA, "tc2": _lib.NCE_CTA_PAIR}
+    return {"auto": _lib.NCE_AUTO, "simt": _lib.NCE_FORCE_SIMT, "tc1": _lib.NCE_SINGLE_CTA, "tc2": _lib.NCE_CTA_PAIR,
+            # measured alternatives kept selectable (profiles/README.md): every one must stay parity-green
+            "ts": _lib.NCE_SINGLE_CTA | _lib.NCE_STATS_TS, "e8": _lib.NCE_SINGLE_CTA | _lib.NCE_EPI8,
+            "dq1": _lib.NCE_SINGLE_CTA | _lib.NCE_DQ_V1, "share2": _lib.NCE_SINGLE_CTA | _lib.NCE_SHARE2,
+            "share4": _lib.NCE_SINGLE_CTA | _lib.NCE_SHARE4}
 
 
 @pytest.fixture(scope="module")
@@ -37,7 +41,7 @@ def test_library_is_the_cuda_one():
     assert major.value == 10 and sm.value >= 100, "expected a Blackwell (sm_100) device"
 
 
-@pytest.mark.parametrize("flag", ["auto", "simt", "tc1", "tc2"])
+@pytest.mark.parametrize("flag", ["auto", "simt", "tc1", "tc2", "ts", "e8", "dq1", "share2"])
 @pytest.mark.parametrize("name", ["c1head", "wrap", "c256", "ragged"])
 def test_golden_dense_api(contrast_golden, name, flag):
     """Unchanged reference call-site (train.py:262-264,273): contrast(q,k,k_all) -> criterion(out)
@@ -110,8 +114,8 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("flag", ["tc1", "tc2"])
-@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("flag,case", [(f, c) for c in CASES for f in ("tc1", "tc2")] +
+                         [("ts", "c3"), ("e8", "c3"), ("dq1", "c3"), ("share2", "c3"), ("share4", "c5"), ("ts", "k126689")])
 def test_fused_vs_oracle(case, flag):
     from moco_b200.NCE import MemoryMoCo
     N, C, K, T = CASES[case]
