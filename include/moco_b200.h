@@ -50,7 +50,8 @@ enum {
     MOCO_NCE_SHARE4 = 16,      /* same with 4-CTA clusters                                            */
     MOCO_NCE_DQ_V1 = 32,       /* first-generation dq kernel (P through shared memory)                */
     MOCO_NCE_STATS_TS = 64,    /* statistics kernel with the q block in TMEM (192-row tiles)          */
-    MOCO_NCE_EPI8 = 128        /* 8 epilogue warps instead of two ping-pong groups of 8               */
+    MOCO_NCE_EPI8 = 128,       /* 8 epilogue warps instead of two ping-pong groups of 8               */
+    MOCO_NCE_KPS1 = 256        /* CTA-pair statistics kernel: one 64-wide K chunk per smem stage (not 2) */
 };
 
 int moco_abi_version(void);
@@ -99,10 +100,6 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype,
  * kernel; MOCO_PROF_DQ: the dq kernel).  Pass NULLs to clear.  Not thread-safe. */
 enum { MOCO_PROF_STATS = 1, MOCO_PROF_DQ = 2 };
 int moco_prof_set_events(int kernel, void* ev_start, void* ev_stop);
-/* Bring-up only: with env MOCO_DEBUG_MODE & 8 the stats kernel leaves per-CTA wait-cycle counters in the
- * workspace; this copies `n_words` 64-bit words of them to the host (synchronous). */
-int moco_debug_read_prof(void* workspace, int N, int C, unsigned long long* out_host, int n_words);
-
 /* Backward of the dense-logits compatibility API (MemoryMoCo.forward returning
  * `out`, then an arbitrary upstream gradient):
  *   dq_i = inv_T * ( g_i0 * k_i + sum_j g_i,1+j * queue_j ),  g = grad_logits [N, K+1] fp32.

@@ -13,7 +13,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_uint3
 from . import build as _build
 
 MOCO_F32, MOCO_BF16 = 0, 1
-NCE_AUTO, NCE_FORCE_SIMT, NCE_CTA_PAIR, NCE_SINGLE_CTA, NCE_SHARE2, NCE_SHARE4, NCE_DQ_V1, NCE_STATS_TS, NCE_EPI8 = 0, 1, 2, 4, 8, 16, 32, 64, 128
+NCE_AUTO, NCE_FORCE_SIMT, NCE_CTA_PAIR, NCE_SINGLE_CTA, NCE_SHARE2, NCE_SHARE4, NCE_DQ_V1, NCE_STATS_TS, NCE_EPI8, NCE_KPS1 = 0, 1, 2, 4, 8, 16, 32, 64, 128, 256
 GATHER_AUTO, GATHER_LDG = 0, 1
 
 # every symbol include/moco_b200.h declares: name -> (restype, argtypes)
@@ -26,7 +26,6 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_size_t, c_int, c_void_p]),
     "moco_prof_set_events": (c_int, [c_int, c_void_p, c_void_p]),
-    "moco_debug_read_prof": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int]),
     "moco_nce_bwd_dense": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
                                    c_void_p, c_void_p]),
     "moco_queue_enqueue": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_void_p]),

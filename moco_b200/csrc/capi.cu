@@ -119,6 +119,7 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
         const int max_share = (flags & MOCO_NCE_SHARE4) ? 4 : ((flags & MOCO_NCE_SHARE2) ? 2 : 1);
         p.max_share = max_share;
         p.epi_warps = (flags & MOCO_NCE_EPI8) ? 8 : 16;
+        p.kps1 = (flags & MOCO_NCE_KPS1) ? 1 : 0;
         p.slices = 0; p.n_pad = 0;
         prof_mark(MOCO_PROF_STATS, 0, stream);
         e = (flags & MOCO_NCE_STATS_TS) ? launch_nce_stats3(p, p.epi_warps, ws, stream) : launch_nce_tc(p, ws, stream);
@@ -147,12 +148,6 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
     e = launch_simt_rows(qb, k, qk_dtype, queue, N, C, K, inv_T, logits, lse, loss_rows, prob_rows, loss_prob, dq, ws, stream);
     if (e != cudaSuccess) return cuda_fail("generic NCE kernel", e);
     return MOCO_OK;
-}
-
-int moco_debug_read_prof(void* workspace, int N, int C, unsigned long long* out_host, int n_words) {
-    NceWorkspace ws = carve_workspace(workspace, N, C);
-    cudaError_t e = cudaMemcpy(out_host, ws.part_o, sizeof(unsigned long long) * (size_t)n_words, cudaMemcpyDeviceToHost);
-    return e == cudaSuccess ? MOCO_OK : MOCO_ERR_CUDA;
 }
 
 int moco_prof_set_events(int kernel, void* ev_start, void* ev_stop) {
@@ -245,6 +240,7 @@ int moco_nce_shard_stats(const void* q_all, const void* k_all, int qk_dtype, con
     p.num_sms = d.sms;
     p.max_share = (flags & MOCO_NCE_SHARE4) ? 4 : ((flags & MOCO_NCE_SHARE2) ? 2 : 1);
     p.epi_warps = (flags & MOCO_NCE_EPI8) ? 8 : 16;
+    p.kps1 = (flags & MOCO_NCE_KPS1) ? 1 : 0;
     p.slices = 0; p.n_pad = 0;
     e = (flags & MOCO_NCE_STATS_TS) ? launch_nce_stats3(p, p.epi_warps, ws, stream) : launch_nce_tc(p, ws, stream);
     if (e != cudaSuccess) return cuda_fail("tcgen05 stats kernel", e);

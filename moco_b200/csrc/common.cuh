@@ -74,6 +74,7 @@ struct NceTcParams {
     int num_sms;
     int max_share;                 // upper bound on the TMA-multicast cluster size (1, 2 or 4)
     int epi_warps;                 // 8 or 16 epilogue warps
+    int kps1;                      // 1: CTA-pair kernel with one (instead of two) K chunks per smem stage
     // outputs of the launch decision
     int slices;
     int n_pad;

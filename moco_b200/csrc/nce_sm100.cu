@@ -1,17 +1,23 @@
 // tcgen05 / TMEM / TMA kernels of the InfoNCE head (sm_100a only).
 //
-//  nce_stats_kernel<G>   S = q . Queue^T on tcgen05 (cta_group::G), accumulators double-buffered in
+//  nce_stats_kernel<G,CS,EW,KPS>  S = q . Queue^T on tcgen05 (cta_group::G), accumulators double-buffered in
 //                        TMEM, epilogue = x/T, online log-sum-exp per row (and optional dense logits).
 //                        Replaces torch.mm + cat + div + CrossEntropyLoss + softmax
 //                        (moco/NCE/Contrast.py:25-27, NCECriterion.py:11-13, train.py:264).
-//  nce_dq_kernel         second pass with the exact lse: S tile -> P = exp(S/T - lse) (bf16, smem)
-//                        -> O += P . Queue on tcgen05 (queue tile reused from smem as an MN-major B
-//                        operand).  Replaces autograd's backward GEMM (train.py:273) and the queue
+//  nce_dq_kernel<CS>     first-generation dq pass (P through shared memory); the default dq pass is
+//                        nce_dq2_sm100.cu.  Replaces autograd's backward GEMM (train.py:273) and the queue
 //                        clone it needs (Contrast.py:24-25).
 //
 // Data layout: q [N, C] bf16 and queue [K, C] bf16 are row-major in HBM ("K-major" for the S GEMM).
 // TMA stages [rows x 64 elements] boxes (128 B per row, 128B swizzle) into shared memory; a tile of
 // R rows is stored as C/64 slabs of R x 128 B.
+//
+// What the measurements on B200 say about this shape of kernel (profiles/README.md):
+//  * one thread can keep the tensor pipe 100 % busy, but only just: a tcgen05.mma costs the issuing thread
+//    ~105 cycles and the issue queue is ~3 MMAs deep, so every other instruction in the issue loop counts;
+//  * tcgen05.ld drains 175-460 B/clk/SM (4-16 warps), MUFU.EX2 sustains 15.8/clk/SM;
+//  * L2 -> SM delivery saturates near 6.3 KB/clk chip-wide; TMA multicast across <= 4 CTAs does not relieve it,
+//    CTA pairs (cta_group::2) do.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -32,20 +38,24 @@ struct StatsArgs {
     float inv_T;
     float* logits;        // optional [N, K+1]
     float2* part_ms;      // [slices, n_pad]
-    int debug;            // bring-up only (env MOCO_DEBUG_MODE): 1 = no epilogue math, 2 = no MMA issue, 4 = no TMA
-    unsigned long long* prof;   // bring-up only (MOCO_DEBUG_MODE & 8): per-CTA wait-cycle counters [8]
+    int debug;            // bring-up only (env MOCO_DEBUG_MODE & 1): skip the epilogue math (tools/pipe_probe.py)
 };
 
 // G  = tcgen05 cta_group (1: M = 128 per CTA; 2: M = 256 per CTA pair, B tile split across the pair)
 // CS = CTAs per cluster that handle DIFFERENT q row blocks but the SAME queue tiles (G == 1 only): each
 //      loads 1/CS of every queue tile and TMA-multicasts it to all CS CTAs, dividing L2->SM traffic by CS.
-template <int G, int CS, int EW>
+// KPS = 64-wide K chunks per shared-memory stage (1 or 2).  The MMA-issuing thread needs ~105 cycles per
+//       tcgen05.mma it issues plus ~150 cycles of barrier wait / fence / commit per stage (tools/umma_bench.cu,
+//       tools/trace_probe.py); with 4 MMAs (512 tensor cycles) per stage that is more than the stage holds, with
+//       8 it is not.
+template <int G, int CS, int EW, int KPS>
 __global__ void __launch_bounds__(128 + EW * 32, 1)
 nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_queue,
                  const StatsArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr int kStageBytes = (kStatsBN / G) * 128;
+    constexpr int kChunkBytes = (kStatsBN / G) * 128;         // one 64-wide K chunk of this CTA's B rows
+    constexpr int kStageBytes = kChunkBytes * KPS;
     constexpr int kEpiWarps = EW;
     // EW == 8 : one epilogue group, every tile.   EW == 16: two groups of 8 warps in ping-pong -- group p owns
     // accumulator buffer p and drains the tiles of parity p, so the exps of tile t overlap the drain of t+1.
@@ -119,12 +129,16 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             const uint32_t full0 = (G == 2) ? mapa_shared(smem_u32(&full[0]), 0) : 0u;
             int brow = t0 * kStatsBN + (int)rank * (kStatsBN / G) + ((CS > 1) ? (int)crank * (kStatsBN / CS) : 0);
             for (int t = t0; t < t1; ++t, brow += kStatsBN) {
-                for (int kc = 0; kc < kchunks; ++kc) {
+                for (int kc = 0; kc < kchunks; kc += KPS) {
                     mbar_wait(&empty[st], ph ^ 1u);
                     if (rank == 0) mbar_arrive_expect_tx(&full[st], (uint32_t)(kStageBytes * G));
-                    if (G == 2)      tma_load_2d_2sm(&tm_queue, full0 + (uint32_t)st * 8u, dst, kc * 64, brow);
-                    else if (CS > 1) tma_load_2d_mc(&tm_queue, &full[st], dst, kc * 64, brow, kMask);
-                    else             tma_load_2d(&tm_queue, &full[st], dst, kc * 64, brow);
+#pragma unroll
+                    for (int kk = 0; kk < KPS; ++kk) {
+                        uint8_t* d = dst + kk * kChunkBytes;
+                        if (G == 2)      tma_load_2d_2sm(&tm_queue, full0 + (uint32_t)st * 8u, d, (kc + kk) * 64, brow);
+                        else if (CS > 1) tma_load_2d_mc(&tm_queue, &full[st], d, (kc + kk) * 64, brow, kMask);
+                        else             tma_load_2d(&tm_queue, &full[st], d, (kc + kk) * 64, brow);
+                    }
                     dst += kStageBytes;
                     if (++st == NS) { st = 0; ph ^= 1u; dst -= (size_t)NS * kStageBytes; }
                 }
@@ -138,6 +152,7 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             const uint64_t a_desc0 = make_sw128_desc(smem_u32(q_s), 0, 1024);
             const uint64_t b_desc0 = make_sw128_desc(smem_u32(b_s), 0, 1024);
             constexpr uint64_t kStageUnits = (uint64_t)(kStageBytes >> 4), kSlabUnits = (uint64_t)(kSlab >> 4);
+            constexpr uint64_t kChunkUnits = (uint64_t)(kChunkBytes >> 4);
             mbar_wait(qfull, 0);
             tc_fence_after();
             int st = 0;
@@ -149,15 +164,19 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)kStatsBN;
                 uint64_t a_desc = a_desc0;
-                for (int kc = 0; kc < kchunks; ++kc) {
+                for (int kc = 0; kc < kchunks; kc += KPS) {
                     mbar_wait(&full[st], ph);
                     tc_fence_after();
-                    umma_ss<G>(d_tmem, a_desc, b_desc, idesc, (uint32_t)(kc != 0));
-                    umma_ss<G>(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
-                    umma_ss<G>(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
-                    umma_ss<G>(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+#pragma unroll
+                    for (int kk = 0; kk < KPS; ++kk) {
+                        const uint64_t ad = a_desc + (uint64_t)kk * kSlabUnits, bd = b_desc + (uint64_t)kk * kChunkUnits;
+                        umma_ss<G>(d_tmem, ad, bd, idesc, (uint32_t)((kc | kk) != 0));
+                        umma_ss<G>(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                        umma_ss<G>(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                        umma_ss<G>(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                    }
                     if (CS > 1) umma_commit_mc(&empty[st], kMask); else umma_commit<G>(&empty[st]);
-                    a_desc += kSlabUnits;
+                    a_desc += kSlabUnits * KPS;
                     b_desc += kStageUnits;
                     if (++st == NS) { st = 0; ph ^= 1u; b_desc = b_desc0; }
                 }
@@ -168,11 +187,10 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
     } else if (warp >= 4) {
         // ---------------------------------------------------- epilogue (kEpiWarps warps)
-        // Warp w may only touch TMEM lanes 32*(w%4)..+31; the 16 warps form 4 column groups of kEpiCols
-        // accumulator columns each.  A thread owns one q row and kEpiCols columns per tile: it pulls them
-        // into registers with two tcgen05.ld, releases the accumulator buffer immediately (the MMA of tile
-        // t+2 can start while the exps of tile t are still being computed) and folds them into its
-        // running (max, sum) in the log2 domain.
+        // Warp w may only touch TMEM lanes 32*(w%4)..+31.  A thread owns one q row and 128 accumulator columns
+        // of a tile: four 32-column tcgen05.ld, each folded into the thread's running (max, sum) in the log2
+        // domain; the accumulator buffer goes back to the MMA as soon as the last load has landed.  With 16
+        // warps, warps 4-11 serve the even tiles (buffer 0) and warps 12-19 the odd tiles (buffer 1).
         const int quarter = warp & 3;
         const int cgrp = (warp - 4) >> 2;
         const int row_local = quarter * 32 + lane;
@@ -221,11 +239,10 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             }
         };
         int lt = (EW == 16) ? (cgrp >> 1) : 0;
-        long long prof_tfull = 0, prof_e0 = clock64();
         for (int t = t0 + lt; t < t1; t += kTileStep, lt += kTileStep) {
             const int acc = lt & 1;
             const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
-            { long long c0 = clock64(); mbar_wait(&tfull[acc], aph); prof_tfull += clock64() - c0; }
+            mbar_wait(&tfull[acc], aph);
             tc_fence_after();
             const int col = (cgrp & 1) * kEpiCols;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kStatsBN + col);
@@ -247,10 +264,6 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     if (!(a.debug & 1)) fold(r, t * kStatsBN + col + ch * 32);
                 }
             }
-        }
-        if (a.prof && warp == 4 && lane == 0) {
-            a.prof[blockIdx.x * 8 + 3] = (unsigned long long)prof_tfull;
-            a.prof[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - prof_e0);
         }
         // combine the column groups of each row (fixed order), then publish the slice partial
         if (cgrp > 0) red_s[(cgrp - 1) * kRowsPerCta + row_local] = make_float2(m, s);
@@ -516,7 +529,8 @@ cudaError_t launch_nce_tc(NceTcParams& p, const NceWorkspace& ws, cudaStream_t s
     if (!make_tmap(&tm_q, p.q_bf16, p.N, p.C, 128)) return cudaErrorUnknown;
     if (!make_tmap(&tm_queue, p.queue, p.K, p.C, kStatsBN / (G * CS))) return cudaErrorUnknown;
 
-    const int stage_bytes = (kStatsBN / G) * 128;
+    const int KPS = (G == 2 && kchunks % 2 == 0 && p.epi_warps == 16 && !p.kps1) ? 2 : 1;
+    const int stage_bytes = (kStatsBN / G) * 128 * KPS;
     const int fixed = kchunks * kSlab + 4096;     // q tile + barriers/red_s
     int stages = (kSmemBudget - fixed) / stage_bytes;
     if (stages > 8) stages = 8;
@@ -530,27 +544,29 @@ cudaError_t launch_nce_tc(NceTcParams& p, const NceWorkspace& ws, cudaStream_t s
     a.logits = p.logits;
     a.part_ms = ws.part_ms;
     a.debug = debug_mode();
-    a.prof = (a.debug & (8 | 16)) ? reinterpret_cast<unsigned long long*>(ws.part_o) : nullptr;
     auto fill = [](StatsArgs& x, int slices) { x.slices = slices; };
     static KernelCache kc[4];
     const int mgroups = mblks / CS, per_slice = mblks * G;
-    static KernelCache kc16[2];
+    static KernelCache kc16[4];
+    if (G == 2 && KPS == 2)
+        return plan_and_launch(nce_stats_kernel<2, 1, 16, 2>, kc16[2], 128 + 16 * 32, smem, 2, mgroups, per_slice, num_tiles,
+                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
     if (G == 2 && p.epi_warps == 16)
-        return plan_and_launch(nce_stats_kernel<2, 1, 16>, kc16[0], 128 + 16 * 32, smem, 2, mgroups, per_slice, num_tiles,
+        return plan_and_launch(nce_stats_kernel<2, 1, 16, 1>, kc16[0], 128 + 16 * 32, smem, 2, mgroups, per_slice, num_tiles,
                                n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
     if (G == 2)
-        return plan_and_launch(nce_stats_kernel<2, 1, 8>, kc[0], 128 + 8 * 32, smem, 2, mgroups, per_slice, num_tiles,
+        return plan_and_launch(nce_stats_kernel<2, 1, 8, 1>, kc[0], 128 + 8 * 32, smem, 2, mgroups, per_slice, num_tiles,
                                n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
     if (CS == 4)
-        return plan_and_launch(nce_stats_kernel<1, 4, 8>, kc[1], 128 + 8 * 32, smem, 4, mgroups, per_slice, num_tiles,
+        return plan_and_launch(nce_stats_kernel<1, 4, 8, 1>, kc[1], 128 + 8 * 32, smem, 4, mgroups, per_slice, num_tiles,
                                n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
     if (CS == 2)
-        return plan_and_launch(nce_stats_kernel<1, 2, 8>, kc[2], 128 + 8 * 32, smem, 2, mgroups, per_slice, num_tiles,
+        return plan_and_launch(nce_stats_kernel<1, 2, 8, 1>, kc[2], 128 + 8 * 32, smem, 2, mgroups, per_slice, num_tiles,
                                n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
     if (p.epi_warps == 16)
-        return plan_and_launch(nce_stats_kernel<1, 1, 16>, kc16[1], 128 + 16 * 32, smem, 1, mgroups, per_slice, num_tiles,
+        return plan_and_launch(nce_stats_kernel<1, 1, 16, 1>, kc16[1], 128 + 16 * 32, smem, 1, mgroups, per_slice, num_tiles,
                                n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
-    return plan_and_launch(nce_stats_kernel<1, 1, 8>, kc[3], 128 + 8 * 32, smem, 1, mgroups, per_slice, num_tiles, n_pad,
+    return plan_and_launch(nce_stats_kernel<1, 1, 8, 1>, kc[3], 128 + 8 * 32, smem, 1, mgroups, per_slice, num_tiles, n_pad,
                            &p.slices, stream, tm_q, tm_queue, a, fill);
 }
 

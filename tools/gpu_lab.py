@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 
 FLAGS = {"auto": 0, "simt": 1, "tc2": 2, "tc1": 4, "tc1_nomc": 4, "tc1_s2": 12, "tc1_s4": 20,
          "dq2": 4, "dq2_nomc": 4, "dq2_s2": 12, "dq2_s4": 20, "dq1": 36, "v1": 4, "e16": 4, "e8": 132, "ts": 68,
-         "ts8": 196, "v1e16": 4, "tc2e16": 2, "tc2e8": 130}
+         "ts8": 196, "v1e16": 4, "tc2e16": 2, "tc2e8": 130, "tc2kps1": 258}
 # name: (N, C, K, T, flagname, want_logits, timing_iters)
 NCE_CASES = {
     "simt_small": (32, 128, 1024, 0.07, "simt", True, 0),
@@ -38,6 +38,7 @@ NCE_CASES = {
     "s4_c4": (2048, 128, 16384, 0.07, "tc1_s4", False, 20),
     "s4_ragged": (500, 192, 3000, 0.1, "tc1_s4", True, 0),
     "tc1_ragged2": (300, 64, 5000, 0.1, "tc1", True, 0),
+    "tc2kps1_c5": (512, 256, 262144, 0.07, "tc2kps1", False, 10),
     "e8_c5": (512, 256, 262144, 0.07, "e8", False, 10),
     "ts_c5": (512, 256, 262144, 0.07, "ts", False, 10),
     "dq1_c5": (512, 256, 262144, 0.07, "dq1", False, 10),
