@@ -313,8 +313,9 @@ def run_native(args):
         "traffic": NCU_TRAFFIC_BYTES.get((N, C, K)),
         "dq_kernel": {"us_per_launch": us_dq, "achieved": 2 * flops / (us_dq * 1e-6) / 1e12, "unit": "TFLOP/s",
                       "frac": 2 * flops / (us_dq * 1e-6) / 1e12 / peaks["tf_sustained"]},
-        "note": "ideal time for this config is < 1 us (1.07 GFLOP / 4.2 MB): launch + pipeline fill bound; "
-                "see roofline_stress for the tensor-bound shape",
+        "note": f"ideal time for this shape is {flops / (peaks['tf_sustained'] * 1e12) * 1e6:.1f} us "
+                f"({flops / 1e9:.2f} GFLOP, {bytes_ / 1e6:.1f} MB): launch + prologue + pipeline fill bound; "
+                "roofline_stress (N=1 runs) is the tensor-bound shape of BASELINE configs[4]",
     }
     line = {
         "metric": "MoCo pretrain images/sec (device-timed, max over ranks)", "value": value, "unit": "images/s",
