@@ -44,8 +44,8 @@ def parse():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of nce_stats_kernel from the committed
-# `ncu --set full` captures (profiles/r1_nce_c2_ncu_metrics.csv, profiles/r1_nce_c5_ncu_metrics.csv)
-NCU_TRAFFIC_BYTES = {(256, 128, 16384): 4286976, (512, 256, 262144): 134530048 + 3916544}
+# `ncu --set full` captures (profiles/r1_final_nce_c2_ncu_metrics.csv, profiles/r1_final_nce_c5_ncu_metrics.csv)
+NCU_TRAFFIC_BYTES = {(256, 128, 16384): 4287232, (512, 256, 262144): 134522880 + 3844352}
 
 
 def load_peaks():

@@ -48,7 +48,11 @@ struct StatsArgs {
 //       tcgen05.mma it issues plus ~150 cycles of barrier wait / fence / commit per stage (tools/umma_bench.cu,
 //       tools/trace_probe.py); with 4 MMAs (512 tensor cycles) per stage that is more than the stage holds, with
 //       8 it is not.
-template <int G, int CS, int EW, int KPS>
+// DENSE = 1: instantiation for the dense-logits API -- the [N, K+1] fp32 logits are written with full-line
+//       coalesced stores (each 32 x 32 register block is transposed across the warp with shuffles first), not
+//       with one 4-byte store per row per lane.  DENSE = 0 keeps a plain per-lane store for the rarely used
+//       variant kernels and never pays registers for the transpose on the fused path.
+template <int G, int CS, int EW, int KPS, int DENSE>
 __global__ void __launch_bounds__(128 + EW * 32, 1)
 nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_queue,
                  const StatsArgs a) {
@@ -219,7 +223,31 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     s3 += ex2(fmaf(__uint_as_float(r[j + 3]), scale2, -m));
                 }
                 s += (s0 + s1) + (s2 + s3);
-                if (lrow) {
+                if constexpr (DENSE) {
+                    if (a.logits != nullptr) {          // warp-uniform
+                        // 32 x 32 transpose: afterwards v[k] of lane L is logit (row block + k, col0 + L)
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * a.inv_T;
+#pragma unroll
+                        for (int sft = 16; sft >= 1; sft >>= 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if ((j & sft) == 0) {
+                                    const bool hi = (lane & sft) != 0;
+                                    const float send = hi ? v[j] : v[j | sft];
+                                    const float recv = __shfl_xor_sync(0xffffffffu, send, sft);
+                                    if (hi) v[j] = recv; else v[j | sft] = recv;
+                                }
+                            }
+                        }
+                        const int rbase = row0 + quarter * 32;
+                        float* out = a.logits + (size_t)rbase * (a.K + 1) + 1 + col0 + lane;
+#pragma unroll
+                        for (int k2 = 0; k2 < 32; ++k2)
+                            if (rbase + k2 < a.N) out[(size_t)k2 * (a.K + 1)] = v[k2];
+                    }
+                } else if (lrow) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) lrow[col0 + j] = __uint_as_float(r[j]) * a.inv_T;
                 }
@@ -549,24 +577,28 @@ cudaError_t launch_nce_tc(NceTcParams& p, const NceWorkspace& ws, cudaStream_t s
     const int mgroups = mblks / CS, per_slice = mblks * G;
     static KernelCache kc16[4];
     if (G == 2 && KPS == 2)
-        return plan_and_launch(nce_stats_kernel<2, 1, 16, 2>, kc16[2], 128 + 16 * 32, smem, 2, mgroups, per_slice, num_tiles,
+        return plan_and_launch(nce_stats_kernel<2, 1, 16, 2, 0>, kc16[2], 128 + 16 * 32, smem, 2, mgroups, per_slice, num_tiles,
                                n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
     if (G == 2 && p.epi_warps == 16)
-        return plan_and_launch(nce_stats_kernel<2, 1, 16, 1>, kc16[0], 128 + 16 * 32, smem, 2, mgroups, per_slice, num_tiles,
+        return plan_and_launch(nce_stats_kernel<2, 1, 16, 1, 0>, kc16[0], 128 + 16 * 32, smem, 2, mgroups, per_slice, num_tiles,
                                n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
     if (G == 2)
-        return plan_and_launch(nce_stats_kernel<2, 1, 8, 1>, kc[0], 128 + 8 * 32, smem, 2, mgroups, per_slice, num_tiles,
+        return plan_and_launch(nce_stats_kernel<2, 1, 8, 1, 0>, kc[0], 128 + 8 * 32, smem, 2, mgroups, per_slice, num_tiles,
                                n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
     if (CS == 4)
-        return plan_and_launch(nce_stats_kernel<1, 4, 8, 1>, kc[1], 128 + 8 * 32, smem, 4, mgroups, per_slice, num_tiles,
+        return plan_and_launch(nce_stats_kernel<1, 4, 8, 1, 0>, kc[1], 128 + 8 * 32, smem, 4, mgroups, per_slice, num_tiles,
                                n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
     if (CS == 2)
-        return plan_and_launch(nce_stats_kernel<1, 2, 8, 1>, kc[2], 128 + 8 * 32, smem, 2, mgroups, per_slice, num_tiles,
+        return plan_and_launch(nce_stats_kernel<1, 2, 8, 1, 0>, kc[2], 128 + 8 * 32, smem, 2, mgroups, per_slice, num_tiles,
                                n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
+    static KernelCache kc_dense;
+    if (p.epi_warps == 16 && p.logits != nullptr)
+        return plan_and_launch(nce_stats_kernel<1, 1, 16, 1, 1>, kc_dense, 128 + 16 * 32, smem, 1, mgroups, per_slice,
+                               num_tiles, n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
     if (p.epi_warps == 16)
-        return plan_and_launch(nce_stats_kernel<1, 1, 16, 1>, kc16[1], 128 + 16 * 32, smem, 1, mgroups, per_slice, num_tiles,
+        return plan_and_launch(nce_stats_kernel<1, 1, 16, 1, 0>, kc16[1], 128 + 16 * 32, smem, 1, mgroups, per_slice, num_tiles,
                                n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
-    return plan_and_launch(nce_stats_kernel<1, 1, 8, 1>, kc[3], 128 + 8 * 32, smem, 1, mgroups, per_slice, num_tiles, n_pad,
+    return plan_and_launch(nce_stats_kernel<1, 1, 8, 1, 0>, kc[3], 128 + 8 * 32, smem, 1, mgroups, per_slice, num_tiles, n_pad,
                            &p.slices, stream, tm_q, tm_queue, a, fill);
 }
 

@@ -340,3 +340,48 @@ def test_cpu_tensors_fail_loudly():
     mod = MemoryMoCo(64, 32, 0.07)          # never moved to CUDA
     with pytest.raises(RuntimeError, match="CUDA"):
         mod(torch.randn(4, 64), torch.randn(4, 64), torch.randn(4, 64))
+
+
+def test_full_step_matches_cpu_reference_step():
+    """One whole MoCo iteration (train.py:244-283) -- ShuffleBN permute, both encoders, head, backward, SGD,
+    EMA, enqueue -- through MoCoStep on the GPU in fp32 vs. the CPU port of the reference step
+    (oracle/cpu_step.py) from identical weights, queue and images.  Two steps, so the second one sees the
+    enqueued keys and the updated encoders.  fp32 convs on GPU (cuDNN/TF32 off) vs CPU: loose tolerances."""
+    from moco_b200 import encoders
+    from moco_b200.NCE import MemoryMoCo
+    from moco_b200.train_step import MoCoStep
+    from oracle.cpu_step import CpuMoCoStep
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        N, C, K, T = 8, 128, 256, 0.07
+        cpu = CpuMoCoStep("resnet18", C, K, T, batch=N, seed=0)
+        # GPU twin from the same weights / queue (bf16-representable queue so both heads see the same negatives)
+        cpu.contrast.memory[:] = O.bf16_round(cpu.contrast.memory)
+        model = encoders.resnet18(low_dim=C)
+        model.load_state_dict(cpu.model.state_dict())
+        model_ema = encoders.resnet18(low_dim=C)
+        model_ema.load_state_dict(cpu.model_ema.state_dict())
+        contrast = MemoryMoCo(C, K, T)
+        contrast.memory.copy_(torch.from_numpy(cpu.contrast.memory))
+        model, model_ema, contrast = model.cuda(), model_ema.cuda(), contrast.cuda()
+        opt = torch.optim.SGD(model.parameters(), lr=0.03 * N / 256, momentum=0.9, weight_decay=1e-4)
+        step = MoCoStep(model, model_ema, contrast, opt, alpha=0.999, amp_dtype=None, overlap_shuffle=True)
+        g = torch.Generator().manual_seed(5)
+        for it in range(2):
+            inputs = torch.randn(N, 6, 224, 224, generator=g)
+            ref_loss, ref_prob = cpu.step(inputs, epoch=3)
+            x1, x2 = torch.split(inputs.cuda(), [3, 3], dim=1)
+            loss, prob = step(x1.contiguous(), x2.contiguous(), 3)
+            assert abs(float(loss) - ref_loss) < 5e-3 * max(1.0, abs(ref_loss)), (it, float(loss), ref_loss)
+            assert abs(float(prob) - ref_prob) < 2e-2 * ref_prob + 1e-6, (it, float(prob), ref_prob)
+            assert contrast.index == cpu.contrast.index
+        # the queue now holds the same keys in the same ring slots (bf16 working copy ~ fp32 keys)
+        np.testing.assert_allclose(contrast.memory.cpu().numpy(), cpu.contrast.memory, atol=2e-3)
+        # EMA encoder followed the same trajectory
+        w_gpu = next(model_ema.parameters()).detach().cpu().numpy()
+        w_cpu = next(cpu.model_ema.parameters()).detach().numpy()
+        np.testing.assert_allclose(w_gpu, w_cpu, atol=1e-4)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
