@@ -6,8 +6,10 @@
 //              tcgen05.st) and is the A operand of O += P . tile (tile re-used from smem as MN-major B).
 //   O[128, C]  accumulates in TMEM for the whole queue slice.
 //
-// TMEM map (512 columns): q [0, C/2) | O [128, 128 + C) | S/P buffer 0 [384, 448) | S/P buffer 1 [448, 512).
-// Queue tiles are 64 rows x C (C/64 slabs of 64 x 128 B, 128B swizzle), 4-7 stage TMA ring; optional
+// TMEM map (512 columns): q [0, C/2) | O [128, 128 + C) | S/P buffers 0 and 1 in the top 2*BN columns.
+// BN (queue rows per tile) is 128 when C <= 128 and 64 when C = 192/256 (O then needs up to 256 columns);
+// tcgen05.mma with N = 64 only reaches ~48 % of peak (tools/umma_bench.cu), so the wider tile matters.
+// Queue tiles are BN rows x C (C/64 slabs of BN x 128 B, 128B swizzle), 4-8 stage TMA ring; optional
 // TMA-multicast sharing across a cluster of CS CTAs that own different q row blocks.
 // tcgen05 MMAs issued by one thread execute in order, so S(i+2) overwriting the buffer P(i) was read from
 // needs no barrier: the issue order S(i+1), PV(i), S(i+2), PV(i+1), ... is the dependency.
@@ -22,9 +24,8 @@
 
 namespace moco {
 
-constexpr int kDq2BN = 64;
 constexpr int kDq2Threads = 384;          // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 softmax
-constexpr uint32_t kQCol = 0, kOCol2 = 128, kSCol = 384;
+constexpr uint32_t kQCol = 0, kOCol2 = 128;
 
 struct Dq2Args {
     int N, C, K;
@@ -36,7 +37,7 @@ struct Dq2Args {
     int debug;                // bring-up only: 1 = no exps, 2 = no MMA issue, 4 = no TMA
 };
 
-template <int CS>
+template <int CS, int BN>
 __global__ void __launch_bounds__(kDq2Threads, 1)
 nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_constant__ CUtensorMap tm_unused,
                const Dq2Args a) {
@@ -44,7 +45,9 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int kchunks = a.C >> 6;
     const int NS = a.stages;
-    constexpr int kSlab64 = kDq2BN * 128;                 // one [64 rows x 64 bf16] slab
+    constexpr int kDq2BN = BN;
+    constexpr uint32_t kSCol = 512 - 2 * BN;
+    constexpr int kSlab64 = kDq2BN * 128;                 // one [BN rows x 64 bf16] slab
     const int tile_bytes = kchunks * kSlab64;
     uint8_t* v_s = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + (size_t)NS * tile_bytes);
@@ -191,21 +194,27 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
             const int b = i & 1;
             mbar_wait(&s_full[b], (uint32_t)(i >> 1) & 1u);
             tc_fence_after();
-            uint32_t r[32];
-            tmem_ld32(lane_base + kSCol + (uint32_t)(b * kDq2BN + chalf * 32), r);
+            constexpr int kHalf = BN / 2;                 // S columns per thread (32 or 64)
+            uint32_t r[kHalf / 32][32];
+#pragma unroll
+            for (int h = 0; h < kHalf / 32; ++h)
+                tmem_ld32(lane_base + kSCol + (uint32_t)(b * kDq2BN + chalf * kHalf + h * 32), r[h]);
             tmem_ld_wait();
             // both column halves of this lane quarter must have read S before either overwrites it with P
             named_bar_sync(2 + quarter, 64);
-            uint32_t p[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-                if (a.debug & 1) { p[j >> 1] = r[j]; continue; }
-                float e0 = ex2(fmaf(__uint_as_float(r[j]), scale2, -lse2));
-                float e1 = ex2(fmaf(__uint_as_float(r[j + 1]), scale2, -lse2));
-                __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
-                p[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+            for (int h = 0; h < kHalf / 32; ++h) {
+                uint32_t p[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    if (a.debug & 1) { p[j >> 1] = r[h][j]; continue; }
+                    float e0 = ex2(fmaf(__uint_as_float(r[h][j]), scale2, -lse2));
+                    float e1 = ex2(fmaf(__uint_as_float(r[h][j + 1]), scale2, -lse2));
+                    __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
+                    p[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                }
+                tmem_st16(lane_base + kSCol + (uint32_t)(b * kDq2BN + chalf * (kHalf / 2) + h * 16), p);
             }
-            tmem_st16(lane_base + kSCol + (uint32_t)(b * kDq2BN + chalf * 16), p);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -240,14 +249,15 @@ cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* 
     const int mblks = (N + 127) / 128;
     const int CS = pick_share(mblks, max_share);
     if (mblks > num_sms) return cudaErrorNotSupported;
-    const int num_tiles = (K + kDq2BN - 1) / kDq2BN;
+    const int BN = (C <= 128) ? 128 : 64;
+    const int num_tiles = (K + BN - 1) / BN;
     const int n_pad = mblks * 128;
     *n_pad_out = n_pad;
 
     CUtensorMap tm_queue;
-    if (!make_tmap(&tm_queue, queue, K, C, kDq2BN / CS)) return cudaErrorUnknown;
+    if (!make_tmap(&tm_queue, queue, K, C, BN / CS)) return cudaErrorUnknown;
 
-    const int tile_bytes = kchunks * kDq2BN * 128;
+    const int tile_bytes = kchunks * BN * 128;
     int stages = (kSmemBudget - 1024) / tile_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) return cudaErrorNotSupported;
@@ -262,16 +272,20 @@ cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* 
     a.part_o = ws.part_o;
     a.debug = debug_mode();
     auto fill = [](Dq2Args& x, int slices) { x.slices = slices; };
-    static KernelCache kc[3];
+    static KernelCache kc[6];
     const int mgroups = mblks / CS;
-    if (CS == 4)
-        return plan_and_launch(nce_dq2_kernel<4>, kc[0], kDq2Threads, smem, 4, mgroups, mblks, num_tiles, n_pad,
-                               slices_out, stream, tm_queue, tm_queue, a, fill);
-    if (CS == 2)
-        return plan_and_launch(nce_dq2_kernel<2>, kc[1], kDq2Threads, smem, 2, mgroups, mblks, num_tiles, n_pad,
-                               slices_out, stream, tm_queue, tm_queue, a, fill);
-    return plan_and_launch(nce_dq2_kernel<1>, kc[2], kDq2Threads, smem, 1, mgroups, mblks, num_tiles, n_pad,
-                           slices_out, stream, tm_queue, tm_queue, a, fill);
+#define MOCO_DQ2_LAUNCH(CS_, BN_, IDX)                                                                             \
+    return plan_and_launch(nce_dq2_kernel<CS_, BN_>, kc[IDX], kDq2Threads, smem, CS_, mgroups, mblks, num_tiles,   \
+                           n_pad, slices_out, stream, tm_queue, tm_queue, a, fill)
+    if (BN == 128) {
+        if (CS == 4) MOCO_DQ2_LAUNCH(4, 128, 0);
+        if (CS == 2) MOCO_DQ2_LAUNCH(2, 128, 1);
+        MOCO_DQ2_LAUNCH(1, 128, 2);
+    }
+    if (CS == 4) MOCO_DQ2_LAUNCH(4, 64, 3);
+    if (CS == 2) MOCO_DQ2_LAUNCH(2, 64, 4);
+    MOCO_DQ2_LAUNCH(1, 64, 5);
+#undef MOCO_DQ2_LAUNCH
 }
 
 }  // namespace moco
