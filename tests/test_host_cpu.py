@@ -160,3 +160,39 @@ def test_shuffle_pull_plan_world_gt1_gloo(golden_dir, world, n, epoch, tag):
     for r in range(world):
         for key in ("x", "x_shuf", "binds", "feat", "feat_all", "feat_local"):
             np.testing.assert_array_equal(ret[r][key], g[f"{tag}_r{r}_{key}"], err_msg=f"rank {r} {key}")
+
+
+def _shard_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from moco_b200.NCE import ShardedMemoryMoCo
+    torch.manual_seed(3)
+    m = ShardedMemoryMoCo(128, 64, 0.07)
+    ret[rank] = dict(row0=m.shard_row0, rows=m.shard_rows, memory=m.memory.numpy().copy(),
+                     keys=sorted(m.state_dict().keys()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_queue_block_layout_world2_gloo():
+    """ShardedMemoryMoCo host logic at world_size 2: rank r owns ring slots [r*K/W, (r+1)*K/W) and the shards
+    concatenate to exactly the queue the reference's MemoryMoCo would have initialised under the same seed."""
+    from moco_b200.NCE import MemoryMoCo
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_shard_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    torch.manual_seed(3)
+    full = MemoryMoCo(128, 64, 0.07).memory.numpy()
+    assert [ret[r]["row0"] for r in range(2)] == [0, 32] and all(ret[r]["rows"] == 32 for r in range(2))
+    np.testing.assert_array_equal(np.concatenate([ret[0]["memory"], ret[1]["memory"]]), full)
+    assert ret[0]["keys"] == ["memory", "params"]
+    with pytest.raises(ValueError, match="divisible"):
+        # world size 1 here: any K is divisible, so emulate the check directly
+        from moco_b200.NCE import ShardedContrast
+        orig = ShardedContrast._world
+        ShardedContrast._world = lambda: (0, 3)
+        try:
+            ShardedContrast.ShardedMemoryMoCo(128, 64, 0.07)
+        finally:
+            ShardedContrast._world = orig
