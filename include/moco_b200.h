@@ -161,6 +161,24 @@ int moco_queue_enqueue_shard(void* shard_bf16, float* shard_f32_or_null, const v
 int moco_f32_to_bf16(const float* src, void* dst_bf16, size_t n_elems, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Momentum (EMA) update of the key encoder, ONE multi-tensor launch.  Replaces
+ * moment_update (moco/util.py:124-127, called at train.py:277 and, with m = 0,
+ * train.py:133):  for every parameter pair   p_ema = p_ema * m + (1 - m) * p,
+ * evaluated per element as fma(one_minus_m, p, rn(p_ema * m)) -- bit-exact with
+ * the reference's mul_ / add_(alpha) pair.
+ *
+ * segs_dev:         DEVICE array of n_segs records {float* p_ema; const float* p;
+ *                   int64 n_elems;} (24 bytes each; an int64 [n_segs, 3] tensor).
+ * chunk_prefix_dev: DEVICE int32 [n_segs + 1], exclusive prefix of
+ *                   ceil(n_elems / moco_ema_chunk_elems()) per record;
+ *                   n_chunks = chunk_prefix[n_segs].
+ * The caller passes m and (1 - m) both already rounded to fp32 (the reference
+ * computes 1 - m in double precision and rounds once).  fp32 tensors only. */
+int moco_ema_chunk_elems(void);
+int moco_ema_update(const void* segs_dev, const int32_t* chunk_prefix_dev, int n_segs, int n_chunks,
+                    float m, float one_minus_m, void* stream);
+
+/* ------------------------------------------------------------------------
  * ShuffleBN row gather over NVLink peer memory.  Replaces dist_collect +
  * fancy-index (moco/util.py:47-58,74-79,88-91): instead of all_gather-ing every
  * rank's batch and indexing, each rank pulls exactly the rows it needs.

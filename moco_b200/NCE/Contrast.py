@@ -133,12 +133,17 @@ class _FusedNCEWithLogits(torch.autograd.Function):
 class MemoryMoCo(nn.Module):
     """Fixed-size queue with momentum encoder (drop-in for moco.NCE.MemoryMoCo)."""
 
-    def __init__(self, feature_dim, queue_size, temperature=0.07):
+    def __init__(self, feature_dim, queue_size, temperature=0.07, persist_index=False):
         super().__init__()
         self.queue_size = queue_size
         self.temperature = temperature
         self.index = 0
         self.kernel_flags = _lib.NCE_AUTO
+        # The reference never checkpoints `index` (Contrast.py:12; train.py:145,163), so a resumed run restarts
+        # the ring at slot 0.  persist_index=True (extension, SURVEY.md §8 f4) parks the write position in the
+        # otherwise vestigial `params` buffer: same state_dict keys/shapes, the reference ignores the value, and
+        # a reference checkpoint (params == -1) still loads with index 0.  Off by default = reference behaviour.
+        self.persist_index = bool(persist_index)
 
         # same buffers / init / state_dict keys as the reference (Contrast.py:15-18)
         self.register_buffer('params', torch.tensor([-1]))
@@ -149,7 +154,19 @@ class MemoryMoCo(nn.Module):
         self.register_buffer('memory_bf16', torch.empty(0, dtype=torch.bfloat16), persistent=False)
         self._bf16_src = None      # (data_ptr, _version) of `memory` the bf16 copy was built from
         self._scratch = {}
-        self.register_load_state_dict_post_hook(lambda m, keys: m._invalidate())
+        self.register_load_state_dict_post_hook(lambda m, keys: m._after_load())
+
+    # -- checkpoint format (train.py:145,163): keys {'params', 'memory'}, fp32 [K, C] ------------------
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        if self.persist_index:
+            self.params.fill_(int(self.index))
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+
+    def _after_load(self):
+        self._invalidate()
+        if self.persist_index:
+            saved = int(self.params.item())
+            self.index = saved % self.queue_size if saved >= 0 else 0
 
     # -- bf16 working queue -------------------------------------------------
     def _invalidate(self):

@@ -309,6 +309,20 @@ int moco_f32_to_bf16(const float* src, void* dst, size_t n, void* stream_) {
     return MOCO_OK;
 }
 
+int moco_ema_chunk_elems(void) { return ema_chunk_elems(); }
+
+int moco_ema_update(const void* segs, const int32_t* chunk_prefix, int n_segs, int n_chunks, float m, float one_minus_m,
+                    void* stream_) {
+    g_err[0] = 0;
+    if (n_segs < 0 || n_chunks < 0 || ((!segs || !chunk_prefix) && n_segs > 0)) {
+        set_error("moco_ema_update: bad argument");
+        return MOCO_ERR_INVALID;
+    }
+    cudaError_t e = launch_ema(segs, chunk_prefix, n_segs, n_chunks, m, one_minus_m, static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return cuda_fail("ema kernel", e);
+    return MOCO_OK;
+}
+
 int moco_shuffle_gather(const void* const* peers, int world, int rows_per_rank, const int64_t* src_rows, int n_rows,
                         size_t row_bytes, void* dst, int flags, void* stream_) {
     g_err[0] = 0;

@@ -102,7 +102,7 @@ static cudaError_t launch_cluster(Kern kern, int grid, int threads, int smem, in
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (cluster > 1) ? 1 : 0;      // plain launch when no cluster feature is used
     return cudaLaunchKernelEx(&cfg, kern, a, b, args);
 }
 

@@ -240,11 +240,68 @@ def set_bn_train(model):
     model.apply(set_bn_train_helper)
 
 
+class _EmaPlan:
+    """Device-side description of one (model, model_ema) pair for ``moco_ema_update``: an int64 [n, 3] table of
+    {p_ema ptr, p ptr, n_elems} and the int32 chunk prefix.  Walking ``parameters()`` of a ResNet-50 twice costs
+    ~0.3 ms of host time -- six times the kernel -- so the plan keeps weak references to the Parameter objects
+    and re-validates them per call (object still alive, storage not moved); anything else rebuilds the plan."""
+
+    def __init__(self, model, model_ema):
+        import weakref
+        ps, pes = list(model.parameters()), list(model_ema.parameters())
+        if len(ps) != len(pes):
+            raise RuntimeError("moco_b200.util.moment_update: model and model_ema have different parameter counts")
+        for p, pe in zip(ps, pes):
+            if not (pe.is_cuda and p.is_cuda and pe.device == p.device):
+                raise RuntimeError("moco_b200.util.moment_update: parameters must live on one CUDA device "
+                                   "(there is no CPU fallback)")
+            if pe.dtype != torch.float32 or p.dtype != torch.float32 or pe.shape != p.shape \
+                    or not pe.is_contiguous() or not p.is_contiguous():
+                raise RuntimeError("moco_b200.util.moment_update: fp32 contiguous parameter pairs of equal shape "
+                                   "required")
+        self.model_ref = weakref.ref(model)
+        self.refs = [weakref.ref(t) for pair in zip(pes, ps) for t in pair]
+        self.ptrs = [t.data_ptr() for pair in zip(pes, ps) for t in pair]
+        self.n_segs = len(ps)
+        self.device = pes[0].device if pes else None
+        if not pes:
+            return
+        chunk = _lib.load().moco_ema_chunk_elems()
+        prefix = [0]
+        for pe in pes:
+            prefix.append(prefix[-1] + (pe.numel() + chunk - 1) // chunk)
+        self.n_chunks = prefix[-1]
+        table = [(pe.data_ptr(), p.data_ptr(), pe.numel()) for pe, p in zip(pes, ps)]
+        self.segs = torch.tensor(table, dtype=torch.int64).reshape(-1, 3).to(self.device)
+        self.prefix = torch.tensor(prefix, dtype=torch.int32).to(self.device)
+
+    def valid_for(self, model) -> bool:
+        if self.model_ref() is not model:
+            return False
+        for ref, ptr in zip(self.refs, self.ptrs):
+            t = ref()
+            if t is None or t.data_ptr() != ptr:
+                return False
+        return True
+
+
 @torch.no_grad()
 def moment_update(model, model_ema, m):
-    """model_ema = m * model_ema + (1 - m) model (util.py:124-127), as two multi-tensor ops
-    instead of 2 x #params tiny launches."""
-    p_ema = [p.data for p in model_ema.parameters()]
-    p = [p.detach().data for p in model.parameters()]
-    torch._foreach_mul_(p_ema, m)
-    torch._foreach_add_(p_ema, p, alpha=1 - m)
+    """model_ema = m * model_ema + (1 - m) model (util.py:124-127; train.py:133 with m = 0, train.py:277 every
+    step) -- one multi-tensor kernel launch (``moco_ema_update``) instead of 2 x #params tiny ones; per element
+    fma(1 - m, p, rn(p_ema * m)), bit-exact with the reference's ``mul_(m).add_(1 - m, p)``.
+
+    The parameter walk is cached per (model, model_ema) pair; replacing a Parameter object or moving its storage
+    is detected and rebuilds the plan (adding/removing parameters in place is not -- delete
+    ``model_ema._moco_ema_plan`` after such surgery)."""
+    plan = model_ema.__dict__.get("_moco_ema_plan")
+    if plan is None or not plan.valid_for(model):
+        plan = _EmaPlan(model, model_ema)
+        model_ema.__dict__["_moco_ema_plan"] = plan
+    if plan.n_segs == 0:
+        return
+    lib = _lib.load()
+    with torch.cuda.device(plan.device):
+        rc = lib.moco_ema_update(plan.segs.data_ptr(), plan.prefix.data_ptr(), plan.n_segs, plan.n_chunks,
+                                 float(m), float(1 - m), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "moco_ema_update")

@@ -270,3 +270,23 @@ def bf16_round(x: np.ndarray) -> np.ndarray:
 def l2_normalize(x: np.ndarray) -> np.ndarray:
     """moco/models/resnet.py:30-33 -- x / sqrt(sum x^2)."""
     return x / np.sqrt((x * x).sum(axis=1, keepdims=True))
+
+
+# --------------------------------------------------------------------------
+# Momentum update of the key encoder.
+# --------------------------------------------------------------------------
+def moment_update(params: Sequence[np.ndarray], params_ema: Sequence[np.ndarray], m: float) -> List[np.ndarray]:
+    """moco/util.py:124-127: ``p2.data.mul_(m).add_(1 - m, p1)`` per parameter pair.
+
+    fp32 arithmetic as PyTorch evaluates it: ``m`` and ``1 - m`` (computed in double) are each rounded to
+    fp32; ``t = rn(p2 * m)``; ``p2 = fma(1 - m, p1, t)`` (ATen's add-with-alpha is one fused multiply-add on
+    its vectorised CPU path and in its CUDA functor).  The fma is emulated in float64: the product of two
+    fp32 values is exact there and the sum rounds once more to 53 bits before the final fp32 rounding."""
+    m32 = np.float32(m)
+    a32 = np.float32(1 - m)
+    out = []
+    for p, pe in zip(params, params_ema):
+        t = (pe.astype(np.float32) * m32).astype(np.float32)
+        r = t.astype(np.float64) + np.float64(a32) * p.astype(np.float64)
+        out.append(r.astype(np.float32))
+    return out

@@ -128,8 +128,38 @@ def gen_shuffle():
     np.savez_compressed(os.path.join(OUT, "shuffle.npz"), **out)
 
 
+# ------------------------------------------------------------------ EMA (moment_update)
+def gen_ema():
+    from moco.util import moment_update
+    torch.manual_seed(77)
+
+    def make():
+        # odd sizes on purpose: 1-element, non-multiple-of-4 and > one kernel chunk (8192 elements)
+        return torch.nn.Sequential(torch.nn.Conv2d(3, 7, 3), torch.nn.BatchNorm2d(7), torch.nn.Linear(131, 67),
+                                   torch.nn.Linear(1, 1), torch.nn.Linear(95, 33, bias=False))
+    out = {}
+    for tag, m, steps in [("m999", 0.999, 3), ("m99", 0.99, 2), ("m0", 0.0, 1)]:
+        model, model_ema = make(), make()
+        out[f"{tag}_m"] = np.array([m], dtype=np.float64)
+        out[f"{tag}_steps"] = np.array([steps], dtype=np.int64)
+        for i, p in enumerate(model_ema.parameters()):
+            out[f"{tag}_ema0_{i}"] = p.detach().numpy().copy()
+        for s in range(steps):
+            with torch.no_grad():
+                for p in model.parameters():                    # a different "trained" model every step
+                    p.copy_(torch.randn_like(p) * 0.05)
+            for i, p in enumerate(model.parameters()):
+                out[f"{tag}_s{s}_p_{i}"] = p.detach().numpy().copy()
+            moment_update(model, model_ema, m)                  # reference util.py:124-127
+            for i, p in enumerate(model_ema.parameters()):
+                out[f"{tag}_s{s}_ema_{i}"] = p.detach().numpy().copy()
+        out[f"{tag}_n"] = np.array([len(list(model.parameters()))], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "ema.npz"), **out)
+
+
 if __name__ == "__main__":
     _shim()
+    gen_ema()
     gen_shuffle_ids()
     gen_contrast()
     gen_shuffle()

@@ -426,3 +426,73 @@ def test_nce_fwd_is_cuda_graph_capturable():
     torch.cuda.synchronize()
     for key in ("lse", "lr", "pr", "lp", "dq"):
         assert torch.equal(a[key], b[key]), key
+
+
+# ------------------------------------------------------------------ EMA (moment_update, util.py:124-127)
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["m999", "m99", "m0"])
+def test_moment_update_matches_reference_bit_exact(golden_dir, tag):
+    """moco_ema_update on the reference's own inputs: fp32 bit patterns of every EMA parameter after every step."""
+    from moco_b200 import _lib
+    from moco_b200.util import moment_update
+    z = np.load(os.path.join(golden_dir, "ema.npz"))
+    n, m = int(z[f"{tag}_n"][0]), float(z[f"{tag}_m"][0])
+
+    class Bag(torch.nn.Module):
+        def __init__(self, arrs):
+            super().__init__()
+            self.ps = torch.nn.ParameterList([torch.nn.Parameter(torch.from_numpy(a.copy())) for a in arrs])
+    ema = Bag([z[f"{tag}_ema0_{i}"] for i in range(n)]).cuda()
+    model = Bag([z[f"{tag}_s0_p_{i}"] for i in range(n)]).cuda()
+    for s in range(int(z[f"{tag}_steps"][0])):
+        with torch.no_grad():
+            for i, p in enumerate(model.parameters()):
+                p.copy_(torch.from_numpy(z[f"{tag}_s{s}_p_{i}"]))
+        before = _lib.launches
+        moment_update(model, ema, m)
+        assert _lib.launches == before + 1                       # one launch for all tensors
+        for i, p in enumerate(ema.parameters()):
+            got = p.detach().cpu().numpy()
+            np.testing.assert_array_equal(got.view(np.uint32), z[f"{tag}_s{s}_ema_{i}"].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_moment_update_resnet50_unaligned_and_vs_oracle():
+    """Full-size (ResNet-50, 23.8 M parameters) EMA against the oracle, plus views at 4-byte-aligned offsets."""
+    from moco_b200 import encoders
+    from moco_b200.util import moment_update
+    torch.manual_seed(5)
+    model, ema = encoders.resnet50(low_dim=128).cuda(), encoders.resnet50(low_dim=128).cuda()
+    p0 = [p.detach().cpu().numpy() for p in model.parameters()]
+    e0 = [p.detach().cpu().numpy() for p in ema.parameters()]
+    moment_update(model, ema, 0.999)
+    want = O.moment_update(p0, e0, 0.999)
+    for w, p in zip(want, ema.parameters()):
+        np.testing.assert_array_equal(p.detach().cpu().numpy().view(np.uint32), w.view(np.uint32))
+    for a, b in zip(p0, model.parameters()):                      # the query encoder is read-only
+        np.testing.assert_array_equal(a, b.detach().cpu().numpy())
+
+    # misaligned storage offsets (scalar path) and a tail shorter than one vector
+    class Views(torch.nn.Module):
+        def __init__(self, flat, sizes, off):
+            super().__init__()
+            self._flat = flat
+            self._views = []
+            for n in sizes:
+                self._views.append(flat[off:off + n])
+                off += n + 1
+        def parameters(self, recurse=True):
+            return iter(self._views)
+    sizes = [1, 3, 8191, 8193, 20001]
+    fa, fb = torch.randn(40000, device="cuda"), torch.randn(40000, device="cuda")
+    ref_b = fb.clone()
+    va, vb = Views(fa, sizes, 1), Views(fb, sizes, 3)
+    want = O.moment_update([v.cpu().numpy() for v in va.parameters()], [v.cpu().numpy() for v in vb.parameters()], 0.99)
+    moment_update(va, vb, 0.99)
+    touched = torch.zeros(40000, dtype=torch.bool)
+    off = 3
+    for n, w, v in zip(sizes, want, vb.parameters()):
+        np.testing.assert_array_equal(v.cpu().numpy().view(np.uint32), w.view(np.uint32))
+        touched[off:off + n] = True
+        off += n + 1
+    assert torch.equal(fb.cpu()[~touched], ref_b.cpu()[~touched])     # nothing outside the views was written

@@ -196,3 +196,40 @@ def test_sharded_queue_block_layout_world2_gloo():
             ShardedContrast.ShardedMemoryMoCo(128, 64, 0.07)
         finally:
             ShardedContrast._world = orig
+
+
+def test_moment_update_has_no_cpu_fallback():
+    """The EMA update is a CUDA kernel behind the C ABI; CPU parameters must raise, not silently run in torch."""
+    import torch
+    from moco_b200.util import moment_update
+    a, b = torch.nn.Linear(4, 3), torch.nn.Linear(4, 3)
+    before = b.weight.detach().clone()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        moment_update(a, b, 0.999)
+    assert torch.equal(b.weight.detach(), before)
+    moment_update(torch.nn.Identity(), torch.nn.Identity(), 0.5)      # no parameters: nothing to do
+
+
+def test_persist_index_roundtrip_is_reference_compatible():
+    """§8 f4: optional `index` persistence rides in the vestigial `params` buffer; keys/shapes unchanged."""
+    import torch
+    from moco_b200.NCE import MemoryMoCo
+    ref_like = MemoryMoCo(8, 20, 0.07)                       # default: reference behaviour
+    ref_like.index = 13
+    sd = ref_like.state_dict()
+    assert sorted(sd) == ["memory", "params"] and int(sd["params"]) == -1
+    fresh = MemoryMoCo(8, 20, 0.07)
+    fresh.load_state_dict(sd)
+    assert fresh.index == 0                                  # the reference restarts the ring on resume
+
+    a = MemoryMoCo(8, 20, 0.07, persist_index=True)
+    a.index = 13
+    sd = a.state_dict()
+    assert sorted(sd) == ["memory", "params"] and sd["params"].shape == (1,) and int(sd["params"]) == 13
+    b = MemoryMoCo(8, 20, 0.07, persist_index=True)
+    b.load_state_dict(sd)
+    assert b.index == 13 and torch.equal(b.memory, a.memory)
+    b.load_state_dict(ref_like.state_dict())                 # a reference checkpoint: params == -1 -> index 0
+    assert b.index == 0
+    fresh.load_state_dict(sd)                                # reference-behaviour module ignores the value
+    assert fresh.index == 0

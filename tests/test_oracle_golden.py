@@ -93,3 +93,15 @@ def test_bf16_round_matches_torch():
     x = np.random.RandomState(0).randn(1000).astype(np.float32) * 3
     ref = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
     np.testing.assert_array_equal(O.bf16_round(x), ref)
+
+
+@pytest.mark.parametrize("tag", ["m999", "m99", "m0"])
+def test_moment_update_bit_exact(golden_dir, tag):
+    """oracle.moment_update vs the reference's util.moment_update (util.py:124-127), fp32 bit patterns."""
+    z = np.load(os.path.join(golden_dir, "ema.npz"))
+    n, m = int(z[f"{tag}_n"][0]), float(z[f"{tag}_m"][0])
+    ema = [z[f"{tag}_ema0_{i}"] for i in range(n)]
+    for s in range(int(z[f"{tag}_steps"][0])):
+        ema = O.moment_update([z[f"{tag}_s{s}_p_{i}"] for i in range(n)], ema, m)
+        for i, a in enumerate(ema):
+            np.testing.assert_array_equal(a.view(np.uint32), z[f"{tag}_s{s}_ema_{i}"].view(np.uint32))
