@@ -45,7 +45,9 @@ def parse():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of nce_stats_kernel from the committed
 # `ncu --set full` captures (profiles/r1_final_nce_c2_ncu_metrics.csv, profiles/r1_final_nce_c5_ncu_metrics.csv)
-NCU_TRAFFIC_BYTES = {(256, 128, 16384): 4287232, (512, 256, 262144): 134522880 + 3844352}
+NCU_TRAFFIC_BYTES = {(256, 128, 16384): 4287232, (512, 256, 262144): 134522880 + 3844352,   # statistics kernel
+                     # one-pass kernel (profiles/r1_onepass_c2_ncu_metrics.csv, r1_onepass_c5_ncu_metrics.csv)
+                     ("onepass", 256, 128, 16384): 4306176, ("onepass", 512, 256, 262144): 134687232 + 5179392}
 
 
 def load_peaks():
@@ -120,7 +122,9 @@ def run_reference(args):
 
 
 def stress_roofline(peaks, dev):
-    """BASELINE configs[4]: N=512, C=256, K=262144 -- q.Queue^T roofline stress on the stats kernel alone."""
+    """BASELINE configs[4]: N=512, C=256, K=262144 -- the tensor-bound shape, hot-path kernels alone (queue 134 MB > L2).
+    Default path = ONE sweep over the queue producing loss statistics AND dq (4NCK FLOP); the two-pass alternative
+    (statistics kernel, then dq kernel that recomputes S: 6NCK FLOP executed, 4NCK credited) is timed beside it."""
     import torch
     import torch.nn.functional as F
     from moco_b200 import _lib
@@ -137,38 +141,45 @@ def stress_roofline(peaks, dev):
     wp = ws.data_ptr() + (-ws.data_ptr()) % 256
     stream = torch.cuda.current_stream().cuda_stream
     iters = 20
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(iters)]
 
-    def call(i):
-        if i >= 0:
-            lib.moco_prof_set_events(1, ev[i][0].cuda_event, ev[i][1].cuda_event)
-            lib.moco_prof_set_events(2, ev[i][2].cuda_event, ev[i][3].cuda_event)
-        rc = lib.moco_nce_fwd(q.data_ptr(), k.data_ptr(), 1, queue.data_ptr(), N, C, K, 1.0 / T, None, lse.data_ptr(),
-                              lr.data_ptr(), pr.data_ptr(), lp.data_ptr(), dq.data_ptr(), wp, wsb, 0, stream)
-        _lib.check(rc, "moco_nce_fwd")
-    for e4 in ev:       # events must exist (be recorded once) before the library records into them
-        for e in e4:
-            e.record()
-    for _ in range(3):
-        call(-1)
-    for i in range(iters):
-        call(i)
-    lib.moco_prof_set_events(1, None, None)
-    lib.moco_prof_set_events(2, None, None)
-    torch.cuda.synchronize()
-    us_stats = sum(e[0].elapsed_time(e[1]) for e in ev) * 1e3 / iters
-    us_dq = sum(e[2].elapsed_time(e[3]) for e in ev) * 1e3 / iters
-    flops = 2.0 * N * C * (K + 1)
-    bytes_ = K * C * 2 + 2 * N * C * 2 + 12 * N
-    a = flops / (us_stats * 1e-6) / 1e12
-    a_dq = 2 * flops / (us_dq * 1e-6) / 1e12
+    def timed_kernels(flags):
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(iters)]
+        for e4 in ev:       # events must exist (be recorded once) before the library records into them; stop before
+            for j in (1, 0, 3, 2):   # start, so a hook that never fires reads as a NEGATIVE interval
+                e4[j].record()
+
+        def call(i):
+            if i >= 0:
+                lib.moco_prof_set_events(1, ev[i][0].cuda_event, ev[i][1].cuda_event)
+                lib.moco_prof_set_events(2, ev[i][2].cuda_event, ev[i][3].cuda_event)
+            rc = lib.moco_nce_fwd(q.data_ptr(), k.data_ptr(), 1, queue.data_ptr(), N, C, K, 1.0 / T, None, lse.data_ptr(),
+                                  lr.data_ptr(), pr.data_ptr(), lp.data_ptr(), dq.data_ptr(), wp, wsb, flags, stream)
+            _lib.check(rc, "moco_nce_fwd")
+        for _ in range(3):
+            call(-1)
+        for i in range(iters):
+            call(i)
+        lib.moco_prof_set_events(1, None, None)
+        lib.moco_prof_set_events(2, None, None)
+        torch.cuda.synchronize()
+        return (sum(e[0].elapsed_time(e[1]) for e in ev) * 1e3 / iters, sum(e[2].elapsed_time(e[3]) for e in ev) * 1e3 / iters)
+
+    _, us_one = timed_kernels(_lib.NCE_AUTO)                      # one-pass kernel reports on the DQ hook
+    us_stats, us_dq = timed_kernels(_lib.NCE_TWO_PASS)
+    flops = 2.0 * N * C * (K + 1)                                 # per direction: fwd = bwd = 2NC(K+1)
+    bytes_ = K * C * 2 + 3 * N * C * 2 + 12 * N
+    a = 2 * flops / (us_one * 1e-6) / 1e12
     return {
-        "workload": "BASELINE configs[4]: N=512 feat_dim=256 K=262144 (stats kernel alone, queue 134 MB > L2)",
+        "workload": "BASELINE configs[4]: N=512 feat_dim=256 K=262144 (hot-path kernels alone, queue 134 MB > L2)",
+        "kernel": "nce_dq2_kernel<FUSED> (one sweep: S=q.Queue^T, P=2^(S/T-m), O+=P.Queue, row sums) -> loss + dq",
         "bound": "tensor", "achieved": a, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": a / peaks["tf_burst"],
-        "us_per_launch": us_stats, "hbm_GBps": bytes_ / (us_stats * 1e-6) / 1e9,
-        "traffic": NCU_TRAFFIC_BYTES.get((N, C, K)),
-        "dq_kernel": {"achieved": a_dq, "unit": "TFLOP/s", "frac": a_dq / peaks["tf_burst"], "us_per_launch": us_dq,
-                      "flops_counted": "4*N*C*K (S recompute + P.Queue, both executed on tcgen05)"},
+        "us_per_launch": us_one, "algorithmic_flops": 2 * flops, "hbm_GBps": bytes_ / (us_one * 1e-6) / 1e9,
+        "traffic": NCU_TRAFFIC_BYTES.get(("onepass", N, C, K)),
+        "two_pass": {"stats_kernel_us": us_stats, "stats_TFLOPs": flops / (us_stats * 1e-6) / 1e12,
+                     "stats_frac": flops / (us_stats * 1e-6) / 1e12 / peaks["tf_burst"],
+                     "dq_kernel_us": us_dq, "dq_TFLOPs_executed": 2 * flops / (us_dq * 1e-6) / 1e12,
+                     "sum_us": us_stats + us_dq,
+                     "note": "statistics pass + dq pass (recomputes S): 6NCK executed for the same 4NCK of algorithmic work"},
     }
 
 
@@ -243,8 +254,8 @@ def run_native(args):
     x1, x2 = split(dev_inputs)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     for e4 in ev:
-        for e in e4:
-            e.record()
+        for j in (1, 0, 3, 2):       # stop before start: a hook that never fires reads as a negative interval
+            e4[j].record()
 
     def loop_resident(steps, profile=False):
         for i in range(steps):
@@ -301,21 +312,25 @@ def run_native(args):
             dist.destroy_process_group()
         return
 
-    flops = 2.0 * N * C * (K + 1)
-    bytes_ = K * C * 2 + 2 * N * C * 2 + 12 * N
-    a_tf = flops / (us_stats * 1e-6) / 1e12
+    # dominant hot-path kernel inside the step: the one-pass kernel (T = 0.07 -> MOCO_NCE_AUTO takes one sweep);
+    # algorithmic work per launch = forward 2NC(K+1) + backward 2NC(K+1) FLOP, queue read once
+    flops = 4.0 * N * C * (K + 1)
+    bytes_ = K * C * 2 + 3 * N * C * 2 + 12 * N
+    one_pass = us_stats <= 0.0                        # the statistics-kernel hook never fired
+    us_main = us_dq if one_pass else us_stats + us_dq
+    a_tf = flops / (us_main * 1e-6) / 1e12
     roofline = {
-        "kernel": "nce_stats_kernel (q.Queue^T on tcgen05 + /T + online log-sum-exp), timed inside the step",
+        "kernel": ("nce_dq2_kernel<FUSED>: one sweep over the queue on tcgen05 (S = q.Queue^T, P = 2^(S/T - m), "
+                   "O += P.Queue, row sums) -> loss statistics + dq" if one_pass else
+                   "nce_stats_kernel + nce_dq2_kernel (two-pass)") + ", timed inside the step",
         "bound": "tensor", "achieved": a_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
         "frac": a_tf / peaks["tf_sustained"], "peak_source": peaks["source"] + ", sustained bf16",
-        "us_per_launch": us_stats, "algorithmic_flops": flops, "algorithmic_bytes": bytes_,
-        "hbm_GBps": bytes_ / (us_stats * 1e-6) / 1e9, "hbm_frac": bytes_ / (us_stats * 1e-6) / 1e9 / peaks["hbm_gbs"],
-        "traffic": NCU_TRAFFIC_BYTES.get((N, C, K)),
-        "dq_kernel": {"us_per_launch": us_dq, "achieved": 2 * flops / (us_dq * 1e-6) / 1e12, "unit": "TFLOP/s",
-                      "frac": 2 * flops / (us_dq * 1e-6) / 1e12 / peaks["tf_sustained"]},
+        "us_per_launch": us_main, "algorithmic_flops": flops, "algorithmic_bytes": bytes_,
+        "hbm_GBps": bytes_ / (us_main * 1e-6) / 1e9, "hbm_frac": bytes_ / (us_main * 1e-6) / 1e9 / peaks["hbm_gbs"],
+        "traffic": NCU_TRAFFIC_BYTES.get(("onepass", N, C, K)),
         "note": f"ideal time for this shape is {flops / (peaks['tf_sustained'] * 1e12) * 1e6:.1f} us "
-                f"({flops / 1e9:.2f} GFLOP, {bytes_ / 1e6:.1f} MB): launch + prologue + pipeline fill bound; "
-                "roofline_stress (N=1 runs) is the tensor-bound shape of BASELINE configs[4]",
+                f"({flops / 1e9:.2f} GFLOP, {bytes_ / 1e6:.1f} MB): two 128-row tiles per CTA, so launch + prologue + "
+                "one pipeline fill dominate; roofline_stress (N=1 runs) is the tensor-bound shape of BASELINE configs[4]",
     }
     line = {
         "metric": "MoCo pretrain images/sec (device-timed, max over ranks)", "value": value, "unit": "images/s",

@@ -51,8 +51,18 @@ enum {
     MOCO_NCE_DQ_V1 = 32,       /* first-generation dq kernel (P through shared memory)                */
     MOCO_NCE_STATS_TS = 64,    /* statistics kernel with the q block in TMEM (192-row tiles)          */
     MOCO_NCE_EPI8 = 128,       /* 8 epilogue warps instead of two ping-pong groups of 8               */
-    MOCO_NCE_KPS1 = 256        /* CTA-pair statistics kernel: one 64-wide K chunk per smem stage (not 2) */
+    MOCO_NCE_KPS1 = 256,       /* CTA-pair statistics kernel: one 64-wide K chunk per smem stage (not 2) */
+    MOCO_NCE_TWO_PASS = 512,   /* statistics pass, then dq pass normalised with the final lse (always exact) */
+    MOCO_NCE_ONE_PASS = 1024   /* loss AND dq from one sweep over the queue (4NCK FLOP, NK exps instead of   */
+                               /* 6NCK, 2NK): each (CTA, row) stabilises with the row maximum of the CTA's   */
+                               /* first tile; exact unless a later logit exceeds that maximum by > ~88 nats, */
+                               /* then that row's loss is inf/NaN (never silently wrong).  AUTO picks it     */
+                               /* when dq is requested, logits are not, and inv_T <= MOCO_ONE_PASS_MAX_INV_T */
+                               /* (L2-normalised q and queue rows of norm <= sqrt(3) -- the reference's      */
+                               /* U(-s, s) initial queue, Contrast.py:16-17 -- then span <= 2 sqrt(3) inv_T  */
+                               /* <= 88 nats); TWO_PASS otherwise.                                            */
 };
+#define MOCO_ONE_PASS_MAX_INV_T 25.0f
 
 int moco_abi_version(void);
 const char* moco_last_error(void);
@@ -98,7 +108,7 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype,
  * events `ev_start` / `ev_stop` (cudaEvent_t) on its stream immediately before /
  * after launching kernel `kernel` (MOCO_PROF_STATS: the q.Queue^T statistics
  * kernel; MOCO_PROF_DQ: the dq kernel).  Pass NULLs to clear.  Not thread-safe. */
-enum { MOCO_PROF_STATS = 1, MOCO_PROF_DQ = 2 };
+enum { MOCO_PROF_STATS = 1, MOCO_PROF_DQ = 2 };   /* one-pass mode: its single kernel reports as MOCO_PROF_DQ */
 int moco_prof_set_events(int kernel, void* ev_start, void* ev_stop);
 /* Backward of the dense-logits compatibility API (MemoryMoCo.forward returning
  * `out`, then an arbitrary upstream gradient):

@@ -14,6 +14,8 @@ from . import build as _build
 
 MOCO_F32, MOCO_BF16 = 0, 1
 NCE_AUTO, NCE_FORCE_SIMT, NCE_CTA_PAIR, NCE_SINGLE_CTA, NCE_SHARE2, NCE_SHARE4, NCE_DQ_V1, NCE_STATS_TS, NCE_EPI8, NCE_KPS1 = 0, 1, 2, 4, 8, 16, 32, 64, 128, 256
+NCE_TWO_PASS, NCE_ONE_PASS = 512, 1024
+ONE_PASS_MAX_INV_T = 25.0          # MOCO_ONE_PASS_MAX_INV_T (include/moco_b200.h)
 GATHER_AUTO, GATHER_LDG = 0, 1
 
 # every symbol include/moco_b200.h declares: name -> (restype, argtypes)
@@ -121,8 +123,11 @@ class _Counting:
             rc = fn(*a)
             if rc == 0:
                 simt = bool(a[16] & NCE_FORCE_SIMT) or a[5] % 64 != 0 or a[5] > 256
-                # prep + (stats + combine [+ dq + dq_reduce]) on the tcgen05 path, prep + row kernel otherwise
-                launches += 2 if simt else (5 if a[13] else 3)
+                one_pass = (a[13] and not a[8] and not (a[16] & (NCE_TWO_PASS | NCE_DQ_V1))
+                            and ((a[16] & NCE_ONE_PASS) or a[7] <= ONE_PASS_MAX_INV_T))
+                # tcgen05 path: prep + one-pass kernel + combine + dq_reduce, or prep + stats + combine
+                # [+ dq + dq_reduce]; generic path: prep + row kernel
+                launches += 2 if simt else (4 if one_pass else (5 if a[13] else 3))
             return rc
         return call
 

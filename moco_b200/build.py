@@ -42,5 +42,17 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_trace_variant():
+    """Lab-only: the same sources with -DMOCO_TRACE (kernel timeline stamps) as libmoco_b200_trace.so."""
+    out = os.path.join(HERE, "libmoco_b200_trace.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-DMOCO_TRACE"] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building the trace variant")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -121,6 +121,25 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
         p.epi_warps = (flags & MOCO_NCE_EPI8) ? 8 : 16;
         p.kps1 = (flags & MOCO_NCE_KPS1) ? 1 : 0;
         p.slices = 0; p.n_pad = 0;
+        // one sweep over the queue for loss + gradient when that is numerically safe (include/moco_b200.h)
+        const bool one_pass = dq && !logits && !(flags & (MOCO_NCE_TWO_PASS | MOCO_NCE_DQ_V1)) &&
+                              ((flags & MOCO_NCE_ONE_PASS) || inv_T <= MOCO_ONE_PASS_MAX_INV_T);
+        if (one_pass) {
+            int slices = 0, n_pad = 0;
+            prof_mark(MOCO_PROF_DQ, 0, stream);
+            e = launch_nce_dq2_tc(qb, queue, N, C, K, inv_T, nullptr, d.sms, max_share, &slices, &n_pad, ws, stream);
+            prof_mark(MOCO_PROF_DQ, 1, stream);
+            if (e == cudaSuccess) {
+                e = launch_combine(N, C, slices, n_pad, inv_T, nullptr, K, lse, loss_rows, prob_rows, loss_prob, ws, stream);
+                if (e != cudaSuccess) return cuda_fail("combine kernel", e);
+                e = launch_dq_reduce(N, C, slices, n_pad, inv_T, k, qk_dtype, prob_rows, dq, ws.part_o, stream,
+                                     ws.part_ms, lse);
+                if (e != cudaSuccess) return cuda_fail("dq reduce kernel", e);
+                return MOCO_OK;
+            }
+            if (e != cudaErrorNotSupported) return cuda_fail("tcgen05 one-pass kernel", e);
+            // shape outside the one-pass kernel's envelope: two-pass below
+        }
         prof_mark(MOCO_PROF_STATS, 0, stream);
         e = (flags & MOCO_NCE_STATS_TS) ? launch_nce_stats3(p, p.epi_warps, ws, stream) : launch_nce_tc(p, ws, stream);
         prof_mark(MOCO_PROF_STATS, 1, stream);

@@ -48,7 +48,8 @@ cudaError_t launch_combine(int N, int C, int slices, int n_pad, float inv_T, flo
                            float* lse, float* loss_rows, float* prob_rows, float* loss_prob,
                            const NceWorkspace& ws, cudaStream_t stream);
 cudaError_t launch_dq_reduce(int N, int C, int slices, int n_pad, float inv_T, const void* k, int k_dtype,
-                             const float* prob_rows, float* dq, const float* part_o, cudaStream_t stream);
+                             const float* prob_rows, float* dq, const float* part_o, cudaStream_t stream,
+                             const float2* part_ms = nullptr, const float* lse = nullptr);
 cudaError_t launch_combine_partial(int N, int slices, int n_pad, float2* ms_out, const NceWorkspace& ws,
                                    cudaStream_t stream);
 cudaError_t launch_combine_merge(int N, int world, float inv_T, const float2* ms_all, float* lse, float* loss_rows,

@@ -11,11 +11,21 @@
 // tcgen05.mma with N = 64 only reaches ~48 % of peak (tools/umma_bench.cu), so the wider tile matters.
 // Queue tiles are BN rows x C (C/64 slabs of BN x 128 B, 128B swizzle), 4-8 stage TMA ring; optional
 // TMA-multicast sharing across a cluster of CS CTAs that own different q row blocks.
-// tcgen05 MMAs issued by one thread execute in order, so S(i+2) overwriting the buffer P(i) was read from
-// needs no barrier: the issue order S(i+1), PV(i), S(i+2), PV(i+1), ... is the dependency.
+// Two MMA-issuing threads (S and P.V), see the kernel body; S(i+2) overwriting the buffer PV(i) reads P from is
+// ordered by the s_free mbarrier that PV(i)'s tcgen05.commit arrives on.
 //
 // Replaces autograd's backward GEMM (train.py:273 of bl0/moco) and the queue clone it needs
 // (moco/NCE/Contrast.py:24-25).
+//
+// ONE-PASS mode (template FUSED = true): the same kernel also produces the softmax statistics, so the separate
+// statistics pass (nce_sm100.cu) is not run at all: 4NCK FLOP and NK exponentials for loss + gradient instead
+// of 6NCK and 2NK.  There is no lse to normalise with yet, so each (CTA, row) stabilises with the row maximum
+// of the CTA's FIRST tile, m, and keeps it:  P~ = 2^(x - m), O~ = sum_j P~_j queue_j, l = sum_j P~_j.  The
+// partial (m, l) pairs have exactly the format the statistics kernel writes, so combine_kernel merges them
+// unchanged, and dq_reduce rescales each slice's O~ by 2^(m_slice - lse).  fp32 has 127 binades of headroom:
+// this is exact unless a later logit exceeds the first tile's maximum by more than ~88 nats, in which case the
+// row's sum overflows to inf and the loss is inf/NaN -- loud, never silently wrong.  moco_nce_fwd therefore
+// selects this mode only when 1/T is small enough that L2-normalised features cannot get there (capi.cu).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -24,7 +34,16 @@
 
 namespace moco {
 
-constexpr int kDq2Threads = 384;          // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 softmax
+#ifdef MOCO_TRACE
+// Lab-only timeline trace (tools/trace_probe.py builds a separate library with -DMOCO_TRACE; never in the product
+// build): clock64 stamps of CTA 0's MMA thread (role 0) and one softmax thread per tile group (roles 1, 2).
+__device__ long long g_dq2_trace[3][64][8];
+#define MOCO_TR(role, tile, slot) do { if (blockIdx.x == 0 && (tile) < 64) g_dq2_trace[role][tile][slot] = clock64(); } while (0)
+#else
+#define MOCO_TR(role, tile, slot) do { } while (0)
+#endif
+
+constexpr int kDq2Threads = 640;          // warp0 TMA, warp1 S-MMA, warp2 TMEM alloc, warp3 PV-MMA, warps 4-19 softmax
 constexpr uint32_t kQCol = 0, kOCol2 = 128;
 
 struct Dq2Args {
@@ -32,17 +51,20 @@ struct Dq2Args {
     int mblks, slices, n_pad, num_tiles, stages;
     float inv_T;
     const __nv_bfloat16* q;   // [N, C]
-    const float* lse;         // [N] natural log
+    const float* lse;         // [N] natural log (two-pass mode)
     float* part_o;            // [slices, n_pad, C]
-    int debug;                // bring-up only: 1 = no exps, 2 = no MMA issue, 4 = no TMA
+    float2* part_ms;          // [slices, n_pad] (stabiliser, sum) in the log2 domain (one-pass mode)
 };
 
-template <int CS, int BN>
+template <int CS, int BN, bool FUSED, bool ISS2>
 __global__ void __launch_bounds__(kDq2Threads, 1)
 nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_constant__ CUtensorMap tm_unused,
                const Dq2Args a) {
+    // The __align__(1024) makes the dynamic window start 1 KB aligned (that is the kernel's 1 KB of "static" smem),
+    // so no alignment slack is budgeted; a misaligned base traps instead of running off the end.
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     const int kchunks = a.C >> 6;
     const int NS = a.stages;
     constexpr int kDq2BN = BN;
@@ -57,7 +79,11 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
     uint64_t* p_full = bars + 2 * NS + 2;    // [2]
     uint64_t* o_full = bars + 2 * NS + 4;
     uint64_t* q_ready = bars + 2 * NS + 5;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 6);
+    uint64_t* s_free = bars + 2 * NS + 6;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 8);
+    // one-pass mode: [3][128] floats the four softmax threads of a row exchange through (tile-0 maxima of the two
+    // column halves first, the three non-leading partial sums at the end); 256 + 1536 B <= the 2 KB after the tiles
+    float* exch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr bool kClustered = CS > 1;
@@ -75,7 +101,7 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_queue);
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], CS); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); mbar_init(&s_free[b], 1); }
         mbar_init(o_full, 1);
         mbar_init(q_ready, 4);
         fence_mbar_init();
@@ -96,7 +122,6 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
             uint32_t ph = 0;
             for (int i = 0; i < ntiles; ++i, st = (st + 1 == NS) ? 0 : st + 1, ph ^= (st == 0) ? 1u : 0u) {
                 mbar_wait(&kv_empty[st], ph ^ 1u);
-                if (a.debug & 4) { mbar_arrive(&kv_full[st]); continue; }
                 mbar_arrive_expect_tx(&kv_full[st], (uint32_t)tile_bytes);
                 for (int kc = 0; kc < kchunks; ++kc) {
                     uint8_t* dst = v_s + (size_t)st * tile_bytes + kc * kSlab64;
@@ -110,29 +135,32 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 && !ISS2) {
         if (lane == 0) {
-            // ------------------------------------------------ MMA issuer
+            // ------------------------------------------------ single MMA issuer (C <= 128: latency-chain bound, where
+            // the extra s_free hand-off of the two-issuer form costs more than the issue overlap gains; measured)
             const uint32_t idesc_s = make_idesc_bf16(128, kDq2BN, 0, 0);            // S = q . tile^T   (A: TMEM, B: K-major)
             const uint32_t idesc_o = make_idesc_bf16(128, (uint32_t)a.C, 0, 1);     // O += P . tile    (A: TMEM, B: MN-major)
             mbar_wait(q_ready, 0);
             tc_fence_after();
-            // lean single-thread loops: descriptors built once and advanced by adds, running stage / phase counters
             const uint64_t vk_desc0 = make_sw128_desc(smem_u32(v_s), 0, 1024);          // tile as K-major B (S MMA)
             const uint64_t vm_desc0 = make_sw128_desc(smem_u32(v_s), kSlab64, 1024);    // tile as MN-major B (PV MMA)
             constexpr uint64_t kSlabUnits = (uint64_t)(kSlab64 >> 4);
             const uint64_t tile_units = (uint64_t)(tile_bytes >> 4);
             int s_st = 0; uint32_t s_ph = 0; uint64_t s_vdesc = vk_desc0;
             int o_st = 0; uint64_t o_vdesc = vm_desc0;
+            // tcgen05 MMAs issued by one thread execute in order, so S(i+2) overwriting the buffer PV(i) reads P from
+            // needs no barrier: the issue order S(i+1), PV(i), S(i+2), PV(i+1), ... is the dependency.
             auto issue_s = [&](int i) {
                 const uint32_t b = (uint32_t)i & 1u;
+                MOCO_TR(0, i, 4);
                 mbar_wait(&kv_full[s_st], s_ph);
                 tc_fence_after();
+                MOCO_TR(0, i, 5);
                 const uint32_t d = tmem_base + kSCol + b * (uint32_t)kDq2BN;
                 uint32_t qa = tmem_base + kQCol;
                 uint64_t vd = s_vdesc;
                 for (int kc = 0; kc < kchunks; ++kc) {
-                    if (a.debug & 2) break;
                     umma_ts<1>(d, qa, vd, idesc_s, (uint32_t)(kc != 0));
                     umma_ts<1>(d, qa + 8, vd + 2, idesc_s, 1u);
                     umma_ts<1>(d, qa + 16, vd + 4, idesc_s, 1u);
@@ -140,7 +168,9 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
                     qa += 32;
                     vd += kSlabUnits;
                 }
+                MOCO_TR(0, i, 6);
                 umma_commit<1>(&s_full[b]);
+                MOCO_TR(0, i, 7);
                 s_vdesc += tile_units;
                 if (++s_st == NS) { s_st = 0; s_ph ^= 1u; s_vdesc = vk_desc0; }
             };
@@ -148,31 +178,112 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
             if (ntiles > 1) issue_s(1);
             for (int i = 0; i < ntiles; ++i) {
                 const uint32_t b = (uint32_t)i & 1u;
+                MOCO_TR(0, i, 0);
                 mbar_wait(&p_full[b], ((uint32_t)i >> 1) & 1u);
                 tc_fence_after();
+                MOCO_TR(0, i, 1);
 #pragma unroll
                 for (int kk = 0; kk < kDq2BN / 16; ++kk) {
-                    if (a.debug & 2) break;
-                    // A = P[:, 16kk..16kk+16) : 8 packed TMEM columns;  B = tile rows [16kk, 16kk+16) x C (MN-major)
-                    umma_ts<1>(tmem_base + kOCol2, tmem_base + kSCol + b * (uint32_t)kDq2BN + (uint32_t)(kk * 8),
+                    constexpr int kHalfRows = kDq2BN / 2;
+                    const uint32_t hh = (uint32_t)((kk * 16) / kHalfRows), off = (uint32_t)(((kk * 16) % kHalfRows) >> 1);
+                    umma_ts<1>(tmem_base + kOCol2, tmem_base + kSCol + b * (uint32_t)kDq2BN + hh * (uint32_t)kHalfRows + off,
                                o_vdesc + (uint64_t)(kk * 128), idesc_o, (uint32_t)((i | kk) != 0));
                 }
+                MOCO_TR(0, i, 2);
                 if (CS > 1) umma_commit_mc(&kv_empty[o_st], kMask); else umma_commit<1>(&kv_empty[o_st]);
+                MOCO_TR(0, i, 3);
                 o_vdesc += tile_units;
                 if (++o_st == NS) { o_st = 0; o_vdesc = vm_desc0; }
-                if (i + 2 < ntiles) issue_s(i + 2);      // overwrites buffer b: ordered after PV(i) by the pipe
+                if (i + 2 < ntiles) issue_s(i + 2);
+            }
+            umma_commit<1>(o_full);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer 1 of 2: S = q . tile^T
+            // Two issuing threads (C > 128, BN = 64) because one cannot feed the pipe: a tcgen05.mma costs its issuing
+            // thread ~62-72 cycles whatever N <= 128 is (tools/umma_bench.cu), so the 16 N = 64 S-MMAs + 4 PV MMAs
+            // of a C = 256 tile take one thread ~1,570 cycles against 1,024 cycles of tensor-pipe work; two threads
+            // overlap (umma_bench: 66 -> 53 cycles/MMA aggregate at N = 64, N = 128 reaches 100 %).
+            // The order S(i+2)-after-PV(i) that one in-order thread gave for free is now the s_free barrier.
+            const uint32_t idesc_s = make_idesc_bf16(128, kDq2BN, 0, 0);            // A: TMEM (q), B: K-major tile
+            mbar_wait(q_ready, 0);
+            // lean single-thread loop: descriptors built once and advanced by adds, running stage / phase counters
+            const uint64_t vk_desc0 = make_sw128_desc(smem_u32(v_s), 0, 1024);
+            constexpr uint64_t kSlabUnits = (uint64_t)(kSlab64 >> 4);
+            const uint64_t tile_units = (uint64_t)(tile_bytes >> 4);
+            int s_st = 0; uint32_t s_ph = 0; uint64_t s_vdesc = vk_desc0;
+            for (int i = 0; i < ntiles; ++i) {
+                const uint32_t b = (uint32_t)i & 1u;
+                MOCO_TR(0, i, 4);
+                mbar_wait(&kv_full[s_st], s_ph);
+                if (i >= 2) mbar_wait(&s_free[b], (((uint32_t)i >> 1) - 1u) & 1u);   // PV(i-2) has consumed P in buffer b
+                tc_fence_after();
+                MOCO_TR(0, i, 5);
+                const uint32_t d = tmem_base + kSCol + b * (uint32_t)kDq2BN;
+                uint32_t qa = tmem_base + kQCol;
+                uint64_t vd = s_vdesc;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    umma_ts<1>(d, qa, vd, idesc_s, (uint32_t)(kc != 0));
+                    umma_ts<1>(d, qa + 8, vd + 2, idesc_s, 1u);
+                    umma_ts<1>(d, qa + 16, vd + 4, idesc_s, 1u);
+                    umma_ts<1>(d, qa + 24, vd + 6, idesc_s, 1u);
+                    qa += 32;
+                    vd += kSlabUnits;
+                }
+                MOCO_TR(0, i, 6);
+                umma_commit<1>(&s_full[b]);
+                MOCO_TR(0, i, 7);
+                s_vdesc += tile_units;
+                if (++s_st == NS) { s_st = 0; s_ph ^= 1u; s_vdesc = vk_desc0; }
+            }
+        }
+    } else if (warp == 3 && ISS2) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer 2 of 2: O += P . tile
+            const uint32_t idesc_o = make_idesc_bf16(128, (uint32_t)a.C, 0, 1);     // A: TMEM (P), B: MN-major tile
+            const uint64_t vm_desc0 = make_sw128_desc(smem_u32(v_s), kSlab64, 1024);
+            const uint64_t tile_units = (uint64_t)(tile_bytes >> 4);
+            int o_st = 0; uint32_t o_ph = 0; uint64_t o_vdesc = vm_desc0;
+            for (int i = 0; i < ntiles; ++i) {
+                const uint32_t b = (uint32_t)i & 1u;
+                MOCO_TR(0, i, 0);
+                mbar_wait(&p_full[b], ((uint32_t)i >> 1) & 1u);
+                mbar_wait(&kv_full[o_st], o_ph);          // complete long ago (S(i) read the tile); observed for visibility
+                tc_fence_after();
+                MOCO_TR(0, i, 1);
+#pragma unroll
+                for (int kk = 0; kk < kDq2BN / 16; ++kk) {
+                    // P rows [16kk, 16kk+16) of the tile: column half hh wrote them at the start of ITS S columns
+                    constexpr int kHalfRows = kDq2BN / 2;
+                    const uint32_t hh = (uint32_t)((kk * 16) / kHalfRows), off = (uint32_t)(((kk * 16) % kHalfRows) >> 1);
+                    umma_ts<1>(tmem_base + kOCol2, tmem_base + kSCol + b * (uint32_t)kDq2BN + hh * (uint32_t)kHalfRows + off,
+                               o_vdesc + (uint64_t)(kk * 128), idesc_o, (uint32_t)((i | kk) != 0));
+                }
+                MOCO_TR(0, i, 2);
+                if (CS > 1) umma_commit_mc(&kv_empty[o_st], kMask); else umma_commit<1>(&kv_empty[o_st]);
+                if (i + 2 < ntiles) umma_commit<1>(&s_free[b]);
+                MOCO_TR(0, i, 3);
+                o_vdesc += tile_units;
+                if (++o_st == NS) { o_st = 0; o_ph ^= 1u; o_vdesc = vm_desc0; }
             }
             umma_commit<1>(o_full);
         }
     } else if (warp >= 4) {
-        // ---------------------------------------------------- softmax warps (8) + q staging + O epilogue
-        const int quarter = warp & 3;
-        const int chalf = (warp - 4) >> 2;
+        // ---------------------------------------------------- softmax warps (16) + q staging + O epilogue
+        // Two tile groups (grp = tile parity = S/P buffer) x two column halves x four TMEM lane quarters.  The
+        // per-tile chain (commit -> mbarrier wake -> tcgen05.ld -> exps -> tcgen05.st -> arrive) is ~1,000+ cycles
+        // of latency; with one group it was exposed once per tile and bounded the kernel at C = 128
+        // (profiles/README.md); two groups on alternating tiles overlap it.
+        const int sw = warp - 4;
+        const int quarter = warp & 3;                     // TMEM lanes [32 * quarter, +32)
+        const int chalf = (sw >> 2) & 1;
+        const int grp = sw >> 3;
         const int row_local = quarter * 32 + lane;
         const int grow = row0 + row_local;
         const float scale2 = a.inv_T * kLog2e;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        if (chalf == 0) {
+        if (sw < 4) {
             // q row -> TMEM (A operand layout: lane = row, one 32-bit column = two consecutive bf16 of K)
             const uint4* src = reinterpret_cast<const uint4*>(a.q + (size_t)(grow < a.N ? grow : 0) * a.C);
             for (int c = 0; c < a.C; c += 64) {
@@ -189,49 +300,106 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(q_ready);
         }
-        const float lse2 = (grow < a.N) ? a.lse[grow] * kLog2e : 0.f;
-        for (int i = 0; i < ntiles; ++i) {
-            const int b = i & 1;
-            mbar_wait(&s_full[b], (uint32_t)(i >> 1) & 1u);
-            tc_fence_after();
-            constexpr int kHalf = BN / 2;                 // S columns per thread (32 or 64)
-            uint32_t r[kHalf / 32][32];
+        constexpr int kHalf = BN / 2;                     // S columns per thread (32 or 64), in 32-column chunks
+        const bool ragged = (a.K % BN) != 0;
+        // this thread's columns of S buffer `grp`; its P (bf16 pairs) goes into the FIRST kHalf/2 of those same
+        // columns -- chunk h of P lands on columns chunk h/2 of S occupied, which this thread has already read,
+        // so no thread ever overwrites S another thread still needs (no barrier between the column halves).
+        const uint32_t own = lane_base + kSCol + (uint32_t)(grp * kDq2BN + chalf * kHalf);
+        // stabiliser in the log2 domain: the row's lse (two-pass) or the first tile's row maximum (one-pass)
+        float lse2 = (!FUSED && grow < a.N) ? a.lse[grow] * kLog2e : 0.f;
+        float lsum = 0.f;
+        if (FUSED) {
+            if (grp == 0) {                               // tile 0 lives in buffer 0
+                mbar_wait(&s_full[0], 0);
+                tc_fence_after();
+                const int valid = (ragged && t0 == a.num_tiles - 1) ? (a.K - (t0 * kDq2BN + chalf * kHalf)) : kHalf;
+                float cm = -INFINITY;
 #pragma unroll
-            for (int h = 0; h < kHalf / 32; ++h)
-                tmem_ld32(lane_base + kSCol + (uint32_t)(b * kDq2BN + chalf * kHalf + h * 32), r[h]);
-            tmem_ld_wait();
-            // both column halves of this lane quarter must have read S before either overwrites it with P
-            named_bar_sync(2 + quarter, 64);
+                for (int h = 0; h < kHalf / 32; ++h) {
+                    uint32_t r[32];
+                    tmem_ld32(own + (uint32_t)(h * 32), r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (h * 32 + j < valid) cm = fmaxf(cm, __uint_as_float(r[j]));
+                }
+                exch[chalf * kRowsPerCta + row_local] = cm;
+            }
+            named_bar_sync(2 + quarter, 128);             // the 4 warps (2 groups x 2 halves) of this lane quarter
+            // the first tile always has >= 1 valid column, so at least one of the two maxima is finite
+            lse2 = fmaxf(exch[row_local], exch[kRowsPerCta + row_local]) * scale2;
+            named_bar_sync(2 + quarter, 128);             // everyone has read: exch may be reused for the sums
+        }
+        const bool tracer = (quarter == 0 && chalf == 0 && lane == 0);
+        for (int i = grp; i < ntiles; i += 2) {
+            if (tracer) MOCO_TR(1 + grp, i, 0);
+            mbar_wait(&s_full[grp], (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            if (tracer) MOCO_TR(1 + grp, i, 1);
+            // queue rows beyond K (last tile only) arrive as zeros: they must not enter the statistics
+            const int col0 = (t0 + i) * kDq2BN + chalf * kHalf;
+            const int valid = (ragged && t0 + i == a.num_tiles - 1) ? (a.K - col0) : kHalf;
 #pragma unroll
             for (int h = 0; h < kHalf / 32; ++h) {
+                uint32_t r[32];
+                tmem_ld32(own + (uint32_t)(h * 32), r);
+                tmem_ld_wait();
+                if (tracer && h == 0) MOCO_TR(1 + grp, i, 2);
+                // branch-free straight-line block: 32 FFMA, 32 MUFU.EX2, 16 packs (+ 2 sum chains) the scheduler can
+                // interleave freely -- a per-element branch or select here costs 2x (profiles/README.md)
+                float e[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) e[j] = ex2(fmaf(__uint_as_float(r[j]), scale2, -lse2));
+                if (FUSED && valid < kHalf) {             // ragged last tile only: mask (also keeps inf * 0 out of O)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (h * 32 + j >= valid) e[j] = 0.f;
+                }
                 uint32_t p[16];
+                float s0 = 0.f, s1 = 0.f;
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    if (a.debug & 1) { p[j >> 1] = r[h][j]; continue; }
-                    float e0 = ex2(fmaf(__uint_as_float(r[h][j]), scale2, -lse2));
-                    float e1 = ex2(fmaf(__uint_as_float(r[h][j + 1]), scale2, -lse2));
-                    __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
+                    if (FUSED) { s0 += e[j]; s1 += e[j + 1]; }
+                    __nv_bfloat162 hh = __floats2bfloat162_rn(e[j], e[j + 1]);
                     p[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
                 }
-                tmem_st16(lane_base + kSCol + (uint32_t)(b * kDq2BN + chalf * (kHalf / 2) + h * 16), p);
+                if (FUSED) lsum += s0 + s1;
+                if (tracer && h == 0) MOCO_TR(1 + grp, i, 3);
+                tmem_st16(own + (uint32_t)(h * 16), p);
             }
+            if (tracer) MOCO_TR(1 + grp, i, 4);
             tmem_st_wait();
+            if (tracer) MOCO_TR(1 + grp, i, 5);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[b]);
+            if (lane == 0) mbar_arrive(&p_full[grp]);
+            if (tracer) MOCO_TR(1 + grp, i, 6);
         }
-        // O epilogue
+        if (FUSED) {
+            // publish (stabiliser, sum) of this (slice, row): the four partial sums are added in a fixed order
+            const int part = grp * 2 + chalf;
+            if (part > 0) exch[(part - 1) * kRowsPerCta + row_local] = lsum;
+            named_bar_sync(2 + quarter, 128);
+            if (part == 0)
+                a.part_ms[(size_t)slice * a.n_pad + grow] =
+                    make_float2(lse2, ((lsum + exch[row_local]) + exch[kRowsPerCta + row_local]) + exch[2 * kRowsPerCta + row_local]);
+        }
+        // O epilogue: C/4 columns per warp of a lane quarter when that is a multiple of 32, else C/2 on group 0
         mbar_wait(o_full, 0);
         tc_fence_after();
-        const int ccols = a.C >> 1;
-        float* orow = a.part_o + ((size_t)slice * a.n_pad + grow) * a.C + chalf * ccols;
-        for (int c = 0; c < ccols; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(lane_base + kOCol2 + (uint32_t)(chalf * ccols + c), r);
-            tmem_ld_wait();
+        const bool four = (a.C & 127) == 0;
+        if (four || grp == 0) {
+            const int ccols = four ? (a.C >> 2) : (a.C >> 1);
+            const int cbeg = (four ? (grp * 2 + chalf) : chalf) * ccols;
+            float* orow = a.part_o + ((size_t)slice * a.n_pad + grow) * a.C + cbeg;
+            for (int c = 0; c < ccols; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(lane_base + kOCol2 + (uint32_t)(cbeg + c), r);
+                tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<uint4*>(orow + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<uint4*>(orow + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            }
         }
     }
 
@@ -241,9 +409,11 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
     if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
+// lse == nullptr selects the one-pass mode: the kernel also writes ws.part_ms (see the header comment)
 cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* queue, int N, int C, int K,
                               float inv_T, const float* lse, int num_sms, int max_share, int* slices_out,
                               int* n_pad_out, const NceWorkspace& ws, cudaStream_t stream) {
+    const bool fused = (lse == nullptr);
     if (C % 64 != 0 || C < 64 || C > 256) return cudaErrorNotSupported;
     const int kchunks = C / 64;
     const int mblks = (N + 127) / 128;
@@ -258,10 +428,10 @@ cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* 
     if (!make_tmap(&tm_queue, queue, K, C, BN / CS)) return cudaErrorUnknown;
 
     const int tile_bytes = kchunks * BN * 128;
-    int stages = (kSmemBudget - 1024) / tile_bytes;
+    int stages = (kSmemBudget - 2048) / tile_bytes;      // 2 KB: barriers + the one-pass exchange array
     if (stages > 8) stages = 8;
     if (stages < 2) return cudaErrorNotSupported;
-    const int smem = stages * tile_bytes + 1024 + 1024;
+    const int smem = stages * tile_bytes + 2048;          // + 1 KB static = 227 KB at C = 256 (7 stages)
 
     Dq2Args a;
     a.N = N; a.C = C; a.K = K;
@@ -270,13 +440,20 @@ cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* 
     a.q = q_bf16;
     a.lse = lse;
     a.part_o = ws.part_o;
-    a.debug = debug_mode();
+    a.part_ms = ws.part_ms;
     auto fill = [](Dq2Args& x, int slices) { x.slices = slices; };
-    static KernelCache kc[6];
+    static KernelCache kc[12];
     const int mgroups = mblks / CS;
 #define MOCO_DQ2_LAUNCH(CS_, BN_, IDX)                                                                             \
-    return plan_and_launch(nce_dq2_kernel<CS_, BN_>, kc[IDX], kDq2Threads, smem, CS_, mgroups, mblks, num_tiles,   \
-                           n_pad, slices_out, stream, tm_queue, tm_queue, a, fill)
+    do {                                                                                                           \
+        constexpr bool kIss2 = (BN_ == 64);                                                                        \
+        if (fused)                                                                                                 \
+            return plan_and_launch(nce_dq2_kernel<CS_, BN_, true, kIss2>, kc[6 + IDX], kDq2Threads, smem, CS_,     \
+                                   mgroups, mblks, num_tiles, n_pad, slices_out, stream, tm_queue, tm_queue, a,    \
+                                   fill);                                                                          \
+        return plan_and_launch(nce_dq2_kernel<CS_, BN_, false, kIss2>, kc[IDX], kDq2Threads, smem, CS_, mgroups,   \
+                               mblks, num_tiles, n_pad, slices_out, stream, tm_queue, tm_queue, a, fill);          \
+    } while (0)
     if (BN == 128) {
         if (CS == 4) MOCO_DQ2_LAUNCH(4, 128, 0);
         if (CS == 2) MOCO_DQ2_LAUNCH(2, 128, 1);
@@ -287,5 +464,11 @@ cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* 
     MOCO_DQ2_LAUNCH(1, 64, 5);
 #undef MOCO_DQ2_LAUNCH
 }
+
+#ifdef MOCO_TRACE
+extern "C" int moco_debug_dq2_trace(long long* host_buf) {
+    return (int)cudaMemcpyFromSymbol(host_buf, g_dq2_trace, sizeof(g_dq2_trace));
+}
+#endif
 
 }  // namespace moco

@@ -174,10 +174,13 @@ cudaError_t launch_combine_merge(int N, int world, float inv_T, const float2* ms
     return cudaGetLastError();
 }
 
-// dq_i = inv_T / N * ( sum_slices O_s[i] + (prob_i - 1) k_i )   -- fixed summation order.
+// dq_i = inv_T / N * ( sum_slices w_s O_s[i] + (prob_i - 1) k_i )   -- fixed summation order.
+// w_s = 1 when the dq kernel normalised with the final lse (two-pass); in one-pass mode slice s used its own
+// stabiliser m_s (part_ms[s][i].x, log2 domain) and w_s = 2^(m_s - lse_i) finishes the normalisation here.
 __global__ void dq_reduce_kernel(int N, int C, int slices, int n_pad, float inv_T, const void* __restrict__ k,
                                  int k_dtype, const float* __restrict__ part_o,
-                                 const float* __restrict__ prob_rows, float* __restrict__ dq) {
+                                 const float* __restrict__ prob_rows, float* __restrict__ dq,
+                                 const float2* __restrict__ part_ms, const float* __restrict__ lse) {
     // 256 threads = (C/4 float4 lanes) x groups; group g sums slices g, g+groups, ...; groups are then
     // added in index order (deterministic).
     __shared__ float4 s_part[256];
@@ -187,9 +190,16 @@ __global__ void dq_reduce_kernel(int N, int C, int slices, int n_pad, float inv_
     const int lane = threadIdx.x % lanes, grp = threadIdx.x / lanes;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (grp < groups) {
+        const float lse2 = part_ms ? lse[i] * kLog2e : 0.f;
         for (int s = grp; s < slices; s += groups) {
             float4 v = __ldcs(reinterpret_cast<const float4*>(part_o + ((size_t)s * n_pad + i) * C) + lane);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            if (part_ms) {
+                const float w = ex2(part_ms[(size_t)s * n_pad + i].x - lse2);
+                acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+            } else {
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
         }
         s_part[grp * lanes + lane] = acc;
     }
@@ -216,9 +226,10 @@ __global__ void dq_reduce_kernel(int N, int C, int slices, int n_pad, float inv_
 }
 
 cudaError_t launch_dq_reduce(int N, int C, int slices, int n_pad, float inv_T, const void* k, int k_dtype,
-                             const float* prob_rows, float* dq, const float* part_o, cudaStream_t stream) {
+                             const float* prob_rows, float* dq, const float* part_o, cudaStream_t stream,
+                             const float2* part_ms, const float* lse) {
     if ((C & 3) != 0 || C > 1024) return cudaErrorNotSupported;
-    dq_reduce_kernel<<<N, 256, 0, stream>>>(N, C, slices, n_pad, inv_T, k, k_dtype, part_o, prob_rows, dq);
+    dq_reduce_kernel<<<N, 256, 0, stream>>>(N, C, slices, n_pad, inv_T, k, k_dtype, part_o, prob_rows, dq, part_ms, lse);
     return cudaGetLastError();
 }
 

@@ -255,10 +255,13 @@ class _EmaPlan:
             if not (pe.is_cuda and p.is_cuda and pe.device == p.device):
                 raise RuntimeError("moco_b200.util.moment_update: parameters must live on one CUDA device "
                                    "(there is no CPU fallback)")
+            # element i of p must pair with element i of p_ema in STORAGE order: equal strides + dense storage
+            # (plain contiguous, or channels_last conv weights as the bf16/NHWC encoders keep them)
+            dense = pe.is_contiguous() or (pe.dim() == 4 and pe.is_contiguous(memory_format=torch.channels_last))
             if pe.dtype != torch.float32 or p.dtype != torch.float32 or pe.shape != p.shape \
-                    or not pe.is_contiguous() or not p.is_contiguous():
-                raise RuntimeError("moco_b200.util.moment_update: fp32 contiguous parameter pairs of equal shape "
-                                   "required")
+                    or pe.stride() != p.stride() or not dense:
+                raise RuntimeError("moco_b200.util.moment_update: fp32 parameter pairs of equal shape, equal strides "
+                                   "and dense storage required")
         self.model_ref = weakref.ref(model)
         self.refs = [weakref.ref(t) for pair in zip(pes, ps) for t in pair]
         self.ptrs = [t.data_ptr() for pair in zip(pes, ps) for t in pair]

@@ -20,11 +20,15 @@ TIGHT = 2e-5               # what identical bf16 inputs + fp32 accumulation actu
 
 def _flags():
     from moco_b200 import _lib
-    return {"auto": _lib.NCE_AUTO, "simt": _lib.NCE_FORCE_SIMT, "tc1": _lib.NCE_SINGLE_CTA, "tc2": _lib.NCE_CTA_PAIR,
+    TP = _lib.NCE_TWO_PASS
+    return {"auto": _lib.NCE_AUTO, "simt": _lib.NCE_FORCE_SIMT, "tc1": _lib.NCE_SINGLE_CTA,
+            # one sweep for loss + dq (what AUTO picks at MoCo temperatures) vs statistics pass + dq pass
+            "onepass": _lib.NCE_SINGLE_CTA | _lib.NCE_ONE_PASS, "twopass": _lib.NCE_SINGLE_CTA | TP,
             # measured alternatives kept selectable (profiles/README.md): every one must stay parity-green
-            "ts": _lib.NCE_SINGLE_CTA | _lib.NCE_STATS_TS, "e8": _lib.NCE_SINGLE_CTA | _lib.NCE_EPI8,
-            "dq1": _lib.NCE_SINGLE_CTA | _lib.NCE_DQ_V1, "share2": _lib.NCE_SINGLE_CTA | _lib.NCE_SHARE2,
-            "share4": _lib.NCE_SINGLE_CTA | _lib.NCE_SHARE4}
+            "tc2": _lib.NCE_CTA_PAIR | TP, "ts": _lib.NCE_SINGLE_CTA | _lib.NCE_STATS_TS | TP,
+            "e8": _lib.NCE_SINGLE_CTA | _lib.NCE_EPI8 | TP, "dq1": _lib.NCE_SINGLE_CTA | _lib.NCE_DQ_V1,
+            "share2": _lib.NCE_SINGLE_CTA | _lib.NCE_SHARE2, "share4": _lib.NCE_SINGLE_CTA | _lib.NCE_SHARE4,
+            "share2_2p": _lib.NCE_SINGLE_CTA | _lib.NCE_SHARE2 | TP}
 
 
 @pytest.fixture(scope="module")
@@ -114,8 +118,9 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("flag,case", [(f, c) for c in CASES for f in ("tc1", "tc2")] +
-                         [("ts", "c3"), ("e8", "c3"), ("dq1", "c3"), ("share2", "c3"), ("share4", "c5"), ("ts", "k126689")])
+@pytest.mark.parametrize("flag,case", [(f, c) for c in CASES for f in ("tc1", "twopass", "tc2")] +
+                         [("ts", "c3"), ("e8", "c3"), ("dq1", "c3"), ("share2", "c3"), ("share4", "c5"), ("ts", "k126689"),
+                          ("onepass", "c3"), ("share2_2p", "c3"), ("auto", "c2"), ("auto", "ragged")])
 def test_fused_vs_oracle(case, flag):
     from moco_b200.NCE import MemoryMoCo
     N, C, K, T = CASES[case]
@@ -144,6 +149,58 @@ def test_fused_vs_oracle(case, flag):
     exp = memory.copy()
     exp[O.enqueue_ids(0, min(N, K), K)] = k[: min(N, K)]
     np.testing.assert_array_equal(mod.memory.cpu().numpy(), exp)
+
+
+def _head_gpu(q, k, memory, T, flags):
+    from moco_b200.NCE import MemoryMoCo
+    N, C = q.shape
+    mod = MemoryMoCo(C, memory.shape[0], T)
+    mod.memory.copy_(torch.from_numpy(memory))
+    mod = mod.cuda()
+    mod.kernel_flags = flags
+    qt = torch.from_numpy(q).cuda().requires_grad_(True)
+    kt = torch.from_numpy(k).cuda()
+    l, p = mod.forward_loss(qt, kt, kt)
+    l.backward()
+    return float(l), float(p), qt.grad.cpu().numpy()
+
+
+@pytest.mark.parametrize("flag", ["auto", "onepass", "twopass"])
+def test_low_temperature_both_sweeps(flag):
+    """T = 0.03 (1/T > MOCO_ONE_PASS_MAX_INV_T): AUTO takes the two-pass kernels; the one-pass kernel, forced, is
+    still exact for unit-norm features (logit span 2/T = 67 nats < 88)."""
+    from moco_b200 import _lib
+    rng = np.random.default_rng(11)
+    N, C, K, T = 96, 128, 5000, 0.03
+    q, k, memory = rand_unit(rng, N, C), rand_unit(rng, N, C), rand_unit(rng, K, C)
+    memory[777] = q[5]                                   # a logit at +1/T far from the first tile
+    memory[4999] = -q[6]                                 # and one at -1/T
+    lse, loss, prob, dq = oracle_head_chunked(q, k, memory, T)
+    before = _lib.launches
+    l, p, g = _head_gpu(q, k, memory, T, _flags()[flag])
+    n_launch = _lib.launches - before - 2                # minus f32->bf16 of the queue and the enqueue
+    assert n_launch == (4 if flag == "onepass" else 5), n_launch
+    assert abs(l - loss) < 2e-4 * max(1.0, abs(loss)), (l, loss)
+    assert abs(p - prob) < 1e-3 * prob + 1e-9
+    assert np.abs(g - dq).max() / np.abs(dq).max() < 5e-3
+
+
+def test_one_pass_overflow_is_loud_and_two_pass_is_exact():
+    """Un-normalised q (norm 12) with its exact direction queued in the LAST tile of a queue long enough that every
+    CTA sweeps >= 2 tiles: that logit exceeds its CTA's first-tile maximum by > 88 nats, the documented limit of the
+    one-pass kernel -> non-finite loss (never a finite wrong number); the two-pass kernels are exact on the same
+    inputs."""
+    rng = np.random.default_rng(12)
+    N, C, K, T = 64, 128, 2 * 160 * 128, 0.07
+    q, k, memory = rand_unit(rng, N, C), rand_unit(rng, N, C), rand_unit(rng, K, C)
+    q = O.bf16_round(q * 12.0)
+    memory[K - 7] = O.bf16_round(q[3] / 12.0)
+    lse, loss, prob, dq = oracle_head_chunked(q, k, memory, T)
+    l2, p2, g2 = _head_gpu(q, k, memory, T, _flags()["twopass"])
+    assert abs(l2 - loss) < 2e-4 * max(1.0, abs(loss)), (l2, loss)
+    assert np.abs(g2 - dq).max() / np.abs(dq).max() < 5e-3
+    l1, _, _ = _head_gpu(q, k, memory, T, _flags()["onepass"])
+    assert not np.isfinite(l1)
 
 
 def test_fp32_inputs_are_rounded_to_bf16_exactly_once():
@@ -496,3 +553,22 @@ def test_moment_update_resnet50_unaligned_and_vs_oracle():
         touched[off:off + n] = True
         off += n + 1
     assert torch.equal(fb.cpu()[~touched], ref_b.cpu()[~touched])     # nothing outside the views was written
+
+
+@pytest.mark.gpu
+def test_moment_update_channels_last_parameters():
+    """bench.py / MoCoStep keep the encoders in channels_last: conv weights are dense but not default-contiguous."""
+    from moco_b200 import encoders
+    from moco_b200.util import moment_update
+    torch.manual_seed(6)
+    model = encoders.resnet18(low_dim=128).cuda().to(memory_format=torch.channels_last)
+    ema = encoders.resnet18(low_dim=128).cuda().to(memory_format=torch.channels_last)
+    assert any(not p.is_contiguous() for p in model.parameters())
+    p0 = [p.detach().cpu().numpy() for p in model.parameters()]
+    e0 = [p.detach().cpu().numpy() for p in ema.parameters()]
+    moment_update(model, ema, 0.999)
+    for w, p in zip(O.moment_update(p0, e0, 0.999), ema.parameters()):
+        np.testing.assert_array_equal(p.detach().cpu().numpy().view(np.uint32), w.view(np.uint32))
+    mixed = encoders.resnet18(low_dim=128).cuda()                 # NCHW vs NHWC strides differ: must refuse
+    with pytest.raises(RuntimeError, match="equal strides"):
+        moment_update(mixed, ema, 0.999)

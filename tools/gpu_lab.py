@@ -16,7 +16,8 @@ sys.path.insert(0, ROOT)
 
 FLAGS = {"auto": 0, "simt": 1, "tc2": 2, "tc1": 4, "tc1_nomc": 4, "tc1_s2": 12, "tc1_s4": 20,
          "dq2": 4, "dq2_nomc": 4, "dq2_s2": 12, "dq2_s4": 20, "dq1": 36, "v1": 4, "e16": 4, "e8": 132, "ts": 68,
-         "ts8": 196, "v1e16": 4, "tc2e16": 2, "tc2e8": 130, "tc2kps1": 258}
+         "ts8": 196, "v1e16": 4, "tc2e16": 2, "tc2e8": 130, "tc2kps1": 258,
+         "op": 4 | 1024, "op_s2": 12 | 1024, "op_s4": 20 | 1024, "tp": 4 | 512}
 # name: (N, C, K, T, flagname, want_logits, timing_iters)
 NCE_CASES = {
     "simt_small": (32, 128, 1024, 0.07, "simt", True, 0),
@@ -58,6 +59,24 @@ NCE_CASES = {
     "e16_c3": (256, 128, 65536, 0.07, "e16", False, 20),
     "e16_ragged": (200, 192, 1000, 0.1, "e16", True, 0),
     "v1_ragged": (200, 192, 1000, 0.1, "v1", True, 0),
+    # one sweep for loss + dq ("op") vs statistics pass + dq pass ("tp")
+    "op_small": (32, 128, 1024, 0.07, "op", False, 0),
+    "op_ragged": (200, 192, 1000, 0.1, "op", False, 0),
+    "op_ragged2": (300, 64, 5000, 0.1, "op", False, 0),
+    "op_s4_ragged": (500, 256, 3000, 0.1, "op_s4", False, 0),
+    "op_c2": (256, 128, 16384, 0.07, "op", False, 20),
+    "op_c3": (256, 128, 65536, 0.07, "op", False, 20),
+    "op_c4": (2048, 128, 16384, 0.07, "op", False, 20),
+    "op_c5": (512, 256, 262144, 0.07, "op", False, 10),
+    "op_s2_c5": (512, 256, 262144, 0.07, "op_s2", False, 10),
+    "tp_small": (32, 128, 1024, 0.07, "tp", False, 0),
+    "tp_ragged": (200, 192, 1000, 0.1, "tp", False, 0),
+    "tp_c64": (100, 64, 777, 0.07, "tp", False, 0),
+    "op_c64": (100, 64, 777, 0.07, "op", False, 0),
+    "tp_c4": (2048, 128, 16384, 0.07, "tp", False, 20),
+    "tp_c2": (256, 128, 16384, 0.07, "tp", False, 20),
+    "tp_c3": (256, 128, 65536, 0.07, "tp", False, 20),
+    "tp_c5": (512, 256, 262144, 0.07, "tp", False, 10),
     "dq2_small": (32, 128, 1024, 0.07, "dq2", False, 0),
     "dq2_c64": (100, 64, 777, 0.07, "dq2", False, 0),
     "dq2_ragged": (200, 192, 1000, 0.1, "dq2", False, 0),
@@ -151,7 +170,10 @@ def run_nce(name):
         torch.cuda.synchronize()
         out["stats_kernel_us"] = sum(e[0].elapsed_time(e[1]) for e in ev) * 1e3 / iters
         out["dq_kernel_us"] = sum(e[2].elapsed_time(e[3]) for e in ev) * 1e3 / iters
-        out["stats_tflops"] = 2.0 * N * C * K / (out["stats_kernel_us"] * 1e-6) / 1e12
+        if out["stats_kernel_us"] > 1.0:
+            out["stats_tflops"] = 2.0 * N * C * K / (out["stats_kernel_us"] * 1e-6) / 1e12
+        else:                                   # one-pass mode: no statistics kernel ran
+            del out["stats_kernel_us"]
         out["dq_tflops"] = 4.0 * N * C * K / (out["dq_kernel_us"] * 1e-6) / 1e12
     return out
 

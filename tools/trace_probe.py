@@ -1,0 +1,63 @@
+"""Lab tool: per-tile timeline of the one-pass / dq kernel (CTA 0) from clock64 stamps.
+
+Builds moco_b200/libmoco_b200_trace.so (-DMOCO_TRACE) HERE (needs nvcc), runs one gpu_lab shape on it and prints,
+per tile, the cycle deltas of the MMA-issuing thread and of one softmax thread of each tile group.
+
+    python tools/trace_probe.py build            # in the build container
+    python tools/trace_probe.py run N C K [flags] # on the GPU box
+"""
+import ctypes
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from moco_b200 import build as B
+    if sys.argv[1] == "build":
+        print(B.build_trace_variant())
+        return
+    import torch
+    import torch.nn.functional as F
+    N, C, K = (int(v) for v in sys.argv[2:5])
+    flags = int(sys.argv[5]) if len(sys.argv) > 5 else 4
+    B.LIB = os.path.join(os.path.dirname(B.LIB), "libmoco_b200_trace.so")
+    from moco_b200 import _lib
+    lib = _lib.load()
+    raw = ctypes.CDLL(B.LIB)
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(1)
+    q = F.normalize(torch.randn(N, C, device=dev, generator=g), dim=1).bfloat16()
+    k = F.normalize(torch.randn(N, C, device=dev, generator=g), dim=1).bfloat16()
+    queue = F.normalize(torch.randn(K, C, device=dev, generator=g), dim=1).bfloat16()
+    f32 = dict(dtype=torch.float32, device=dev)
+    lse, lr, pr = (torch.zeros(N, **f32) for _ in range(3))
+    lp, dq = torch.zeros(2, **f32), torch.zeros(N, C, **f32)
+    wsb = lib.moco_nce_workspace_bytes(N, C, K)
+    ws = torch.zeros(wsb + 256, dtype=torch.uint8, device=dev)
+    wp = ws.data_ptr() + (-ws.data_ptr()) % 256
+    for _ in range(3):
+        rc = lib.moco_nce_fwd(q.data_ptr(), k.data_ptr(), 1, queue.data_ptr(), N, C, K, 1 / 0.07, None, lse.data_ptr(),
+                              lr.data_ptr(), pr.data_ptr(), lp.data_ptr(), dq.data_ptr(), wp, wsb, flags,
+                              torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, lib.moco_last_error()
+    torch.cuda.synchronize()
+    buf = (ctypes.c_longlong * (3 * 64 * 8))()
+    assert raw.moco_debug_dq2_trace(buf) == 0
+    t = [[[buf[(r * 64 + i) * 8 + s] for s in range(8)] for i in range(64)] for r in range(3)]
+    base = min(v for r in t for row in r for v in row if v > 0)
+    names = {0: "MMA : waitP  gotP  PVissued commitKV | waitKV gotKV Sissued commitS",
+             1: "SM g0: waitS gotS ld0done st0 allst stwait arrived", 2: "SM g1: (same)"}
+    for r in range(3):
+        print(names[r])
+        for i in range(min(64, 24)):
+            row = t[r][i]
+            if not any(row):
+                continue
+            print(f"  tile {i:2d}: " + " ".join(f"{(v - base) if v else -1:7d}" for v in row))
+
+
+if __name__ == "__main__":
+    main()

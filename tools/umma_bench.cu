@@ -3,6 +3,7 @@
 // matter for timing).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I moco_b200/csrc -o tools/umma_bench tools/umma_bench.cu
 #include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "sm100_ptx.cuh"
@@ -101,7 +102,79 @@ void run(const char* name) {
     cudaFree(cyc);
 }
 
+
+// Two issuing threads (warps 1 and 2), each with its own accumulator and commit barriers: does the ~66-cycle
+// per-instruction issue cost of small-N MMAs belong to the thread or to the SM?
+template <int N, int NI>
+__global__ void __launch_bounds__(384, 1) k2(long long* cycles, int iters) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t bar[2][2];
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < (64 + 128) * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (warp == 0) { tmem_alloc<1>(&slot, 512); tmem_relinquish<1>(); }
+    if (threadIdx.x == 32) { for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) mbar_init(&bar[a][b], 1); fence_mbar_init(); }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = slot;
+    if ((warp == 1 || (warp == 2 && NI == 2)) && lane == 0) {
+        const int me = warp - 1;
+        const uint32_t a_addr = smem_u32(smem);
+        const uint32_t b_addr = smem_u32(smem + 64 * 1024);
+        const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+        long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            const int b = i & 1;
+            if (i >= 2) mbar_wait(&bar[me][b], (uint32_t)((i >> 1) - 1) & 1u);
+            const uint32_t d = tmem + (uint32_t)(me * 256 + b * 128);
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks)
+                umma_ss<1>(d, make_sw128_desc(a_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024),
+                           make_sw128_desc(b_addr + (ks >> 2) * 32768 + (ks & 3) * 32, 0, 1024), idesc, ks != 0);
+            umma_commit<1>(&bar[me][b]);
+        }
+        mbar_wait(&bar[me][(iters - 1) & 1], (uint32_t)((iters - 1) >> 1) & 1u);
+        if (iters > 1) mbar_wait(&bar[me][(iters - 2) & 1], (uint32_t)((iters - 2) >> 1) & 1u);
+        cycles[me * 148 + blockIdx.x] = clock64() - t0;
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<1>(tmem, 512);
+}
+
+template <int N, int NI>
+void run2(const char* name) {
+    int sms = 148, iters = 400;
+    long long* cyc;
+    cudaMalloc(&cyc, sizeof(long long) * sms * 2);
+    cudaMemset(cyc, 0, sizeof(long long) * sms * 2);
+    int smem = (64 + 128) * 1024 + 1024;
+    cudaFuncSetAttribute(k2<N, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int rep = 0; rep < 2; ++rep) {
+        k2<N, NI><<<sms, 384, smem>>>(cyc, iters);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("%-34s ERROR %s\n", name, cudaGetErrorString(e)); exit(1); }
+    }
+    long long h[296];
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double c = 0; for (int i = 0; i < sms; ++i) c += (h[i] > h[148 + i] ? h[i] : h[148 + i]); c /= sms;
+    double per = c / (iters * 16.0 * NI);
+    printf("%-34s issuers=%d N=%3d  %.1f cycles/MMA aggregate (ideal %d) -> %.0f%% of tensor peak\n", name, NI, N, per, N / 2,
+           100.0 * (N / 2) / per);
+    cudaFree(cyc);
+}
+
 int main() {
+    run2<64, 1>("one issuing thread");
+    run2<64, 2>("two issuing threads");
+    run2<128, 1>("one issuing thread");
+    run2<128, 2>("two issuing threads");
+    run2<256, 2>("two issuing threads");
+    if (getenv("UMMA_BENCH_ONLY2")) return 0;
     run<0, 256, 3, 1>("SS + 8 warps polling mbarrier");
     run<0, 256, 3, 2>("SS + 8 warps streaming tcgen05.ld");
     run<0, 256, 3>("SS + wait/fence every 4 MMAs");
