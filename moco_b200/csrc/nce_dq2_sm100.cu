@@ -37,7 +37,7 @@ namespace moco {
 #ifdef MOCO_TRACE
 // Lab-only timeline trace (tools/trace_probe.py builds a separate library with -DMOCO_TRACE; never in the product
 // build): clock64 stamps of CTA 0's MMA thread (role 0) and one softmax thread per tile group (roles 1, 2).
-__device__ long long g_dq2_trace[3][64][8];
+__device__ long long g_dq2_trace[4][64][8];   // role 3, row 0: kernel-level milestones
 #define MOCO_TR(role, tile, slot) do { if (blockIdx.x == 0 && (tile) < 64) g_dq2_trace[role][tile][slot] = clock64(); } while (0)
 #else
 #define MOCO_TR(role, tile, slot) do { } while (0)
@@ -65,6 +65,7 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+    if (threadIdx.x == 0) MOCO_TR(3, 0, 0);                       // kernel entry
     const int kchunks = a.C >> 6;
     const int NS = a.stages;
     constexpr int kDq2BN = BN;
@@ -98,6 +99,19 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
     const int ntiles = t1 - t0;
     const int row0 = mblk * kRowsPerCta;
 
+    // q staging warps (4-7): put the global loads of the first 128 columns of their q row in flight before the
+    // set-up barrier -- at small K (two tiles per CTA) this load's latency was 1.6 us of the kernel's critical path
+    uint4 qpre[16];
+    const int qpre_n = (a.C < 128 ? a.C : 128) >> 3;
+    if (warp >= 4 && warp < 8) {
+        const int grow_q = row0 + (warp & 3) * 32 + lane;
+        const uint4* src = reinterpret_cast<const uint4*>(a.q + (size_t)(grow_q < a.N ? grow_q : 0) * a.C);
+        // unconditional loads from a clamped row (nothing may consume them before the barrier); rows >= N are
+        // zeroed when they are stored to TMEM
+#pragma unroll
+        for (int v = 0; v < 16; ++v)
+            if (v < qpre_n) qpre[v] = __ldg(src + v);
+    }
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_queue);
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], CS); }
@@ -114,6 +128,7 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
     if (kClustered) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) MOCO_TR(3, 0, 1);                       // barriers initialised, TMEM allocated
 
     if (warp == 0) {
         if (lane == 0) {
@@ -286,7 +301,27 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
         if (sw < 4) {
             // q row -> TMEM (A operand layout: lane = row, one 32-bit column = two consecutive bf16 of K)
             const uint4* src = reinterpret_cast<const uint4*>(a.q + (size_t)(grow < a.N ? grow : 0) * a.C);
-            for (int c = 0; c < a.C; c += 64) {
+            {                                             // columns [0, 64): loaded before the set-up barrier
+                uint32_t r[32];
+#pragma unroll
+                for (int v = 0; v < 8; ++v) { r[v * 4 + 0] = qpre[v].x; r[v * 4 + 1] = qpre[v].y; r[v * 4 + 2] = qpre[v].z; r[v * 4 + 3] = qpre[v].w; }
+                if (grow >= a.N) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+                tmem_st32(lane_base + kQCol, r);
+            }
+            if (a.C > 64) {                               // columns [64, 128): idem
+                uint32_t r[32];
+#pragma unroll
+                for (int v = 0; v < 8; ++v) { r[v * 4 + 0] = qpre[8 + v].x; r[v * 4 + 1] = qpre[8 + v].y; r[v * 4 + 2] = qpre[8 + v].z; r[v * 4 + 3] = qpre[8 + v].w; }
+                if (grow >= a.N) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+                tmem_st32(lane_base + kQCol + 32u, r);
+            }
+            for (int c = 128; c < a.C; c += 64) {
                 uint32_t r[32];
 #pragma unroll
                 for (int v = 0; v < 8; ++v) {
@@ -299,6 +334,7 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(q_ready);
+            if (sw == 0 && lane == 0) MOCO_TR(3, 0, 2);           // q staged into TMEM
         }
         constexpr int kHalf = BN / 2;                     // S columns per thread (32 or 64), in 32-column chunks
         const bool ragged = (a.K % BN) != 0;
@@ -387,25 +423,35 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
         // O epilogue: C/4 columns per warp of a lane quarter when that is a multiple of 32, else C/2 on group 0
         mbar_wait(o_full, 0);
         tc_fence_after();
+        if (sw == 0 && lane == 0) MOCO_TR(3, 0, 3);               // last P.V MMA complete
         const bool four = (a.C & 127) == 0;
         if (four || grp == 0) {
             const int ccols = four ? (a.C >> 2) : (a.C >> 1);
             const int cbeg = (four ? (grp * 2 + chalf) : chalf) * ccols;
-            float* orow = a.part_o + ((size_t)slice * a.n_pad + grow) * a.C + cbeg;
+            // A thread owns one row of O in TMEM; storing it directly makes every warp store hit 32 different
+            // 512-byte-strided rows (measured 3.2 us at C = 128).  Each 32 x 32 block goes through a padded
+            // (stride 33, conflict-free both ways) buffer in the now idle tile ring, then out as 128-byte rows.
+            float* tbuf = reinterpret_cast<float*>(v_s) + sw * (32 * 33);
+            float* oblk = a.part_o + ((size_t)slice * a.n_pad + row0 + quarter * 32) * a.C + cbeg + lane;
             for (int c = 0; c < ccols; c += 32) {
                 uint32_t r[32];
                 tmem_ld32(lane_base + kOCol2 + (uint32_t)(cbeg + c), r);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<uint4*>(orow + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+                __syncwarp();
+#pragma unroll
+                for (int k2 = 0; k2 < 32; ++k2) oblk[(size_t)k2 * a.C + c] = tbuf[k2 * 33 + lane];
+                __syncwarp();
             }
         }
     }
 
+    if (warp == 4 && lane == 0) MOCO_TR(3, 0, 4);                 // O written
     __syncwarp();
     tc_fence_before();
     if (kClustered) cluster_sync_all(); else __syncthreads();
+    if (threadIdx.x == 0) MOCO_TR(3, 0, 5);                       // all roles done
     if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 

@@ -44,13 +44,14 @@ def main():
                               torch.cuda.current_stream().cuda_stream)
         assert rc == 0, lib.moco_last_error()
     torch.cuda.synchronize()
-    buf = (ctypes.c_longlong * (3 * 64 * 8))()
+    buf = (ctypes.c_longlong * (4 * 64 * 8))()
     assert raw.moco_debug_dq2_trace(buf) == 0
-    t = [[[buf[(r * 64 + i) * 8 + s] for s in range(8)] for i in range(64)] for r in range(3)]
+    t = [[[buf[(r * 64 + i) * 8 + s] for s in range(8)] for i in range(64)] for r in range(4)]
     base = min(v for r in t for row in r for v in row if v > 0)
     names = {0: "MMA : waitP  gotP  PVissued commitKV | waitKV gotKV Sissued commitS",
-             1: "SM g0: waitS gotS ld0done st0 allst stwait arrived", 2: "SM g1: (same)"}
-    for r in range(3):
+             1: "SM g0: waitS gotS ld0done st0 allst stwait arrived", 2: "SM g1: (same)",
+             3: "KERNEL: entry setup_done q_staged o_full O_written all_done"}
+    for r in range(4):
         print(names[r])
         for i in range(min(64, 24)):
             row = t[r][i]
