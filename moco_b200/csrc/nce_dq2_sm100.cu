@@ -99,6 +99,21 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
     const int ntiles = t1 - t0;
     const int row0 = mblk * kRowsPerCta;
 
+    pdl_launch_dependents();
+    // ---- set-up that touches no global memory (overlaps the predecessor kernel under PDL) ----
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_queue);     // kernel parameter space, not global data
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], CS); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); mbar_init(&s_free[b], 1); }
+        mbar_init(o_full, 1);
+        mbar_init(q_ready, 4);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<1>(tmem_slot, 512);
+        tmem_relinquish<1>();
+    }
+    pdl_wait();                                                   // predecessor complete: q / lse / the queue are final
     // q staging warps (4-7): put the global loads of the first 128 columns of their q row in flight before the
     // set-up barrier -- at small K (two tiles per CTA) this load's latency was 1.6 us of the kernel's critical path
     uint4 qpre[16];
@@ -111,18 +126,6 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
 #pragma unroll
         for (int v = 0; v < 16; ++v)
             if (v < qpre_n) qpre[v] = __ldg(src + v);
-    }
-    if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_queue);
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], CS); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); mbar_init(&s_free[b], 1); }
-        mbar_init(o_full, 1);
-        mbar_init(q_ready, 4);
-        fence_mbar_init();
-    }
-    if (warp == 2) {
-        tmem_alloc<1>(tmem_slot, 512);
-        tmem_relinquish<1>();
     }
     tc_fence_before();
     if (kClustered) cluster_sync_all(); else __syncthreads();
@@ -496,9 +499,9 @@ cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* 
         if (fused)                                                                                                 \
             return plan_and_launch(nce_dq2_kernel<CS_, BN_, true, kIss2>, kc[6 + IDX], kDq2Threads, smem, CS_,     \
                                    mgroups, mblks, num_tiles, n_pad, slices_out, stream, tm_queue, tm_queue, a,    \
-                                   fill);                                                                          \
+                                   fill, true);                                                                    \
         return plan_and_launch(nce_dq2_kernel<CS_, BN_, false, kIss2>, kc[IDX], kDq2Threads, smem, CS_, mgroups,   \
-                               mblks, num_tiles, n_pad, slices_out, stream, tm_queue, tm_queue, a, fill);          \
+                               mblks, num_tiles, n_pad, slices_out, stream, tm_queue, tm_queue, a, fill, true);    \
     } while (0)
     if (BN == 128) {
         if (CS == 4) MOCO_DQ2_LAUNCH(4, 128, 0);

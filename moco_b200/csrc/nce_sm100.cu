@@ -94,6 +94,8 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const int t1 = (int)(((long long)(slice + 1) * a.num_tiles) / a.slices);
     const int row0 = (mblk * G + (int)rank) * kRowsPerCta;
 
+    pdl_launch_dependents();
+    // set-up that touches no global memory: overlaps the predecessor kernel (prep) under PDL
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_queue);
@@ -108,6 +110,7 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tmem_alloc<G>(tmem_slot, 512);
         tmem_relinquish<G>();
     }
+    pdl_wait();                                  // predecessor complete: q_bf16 and the queue are final
     tc_fence_before();
     if (kClustered) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
@@ -578,28 +581,28 @@ cudaError_t launch_nce_tc(NceTcParams& p, const NceWorkspace& ws, cudaStream_t s
     static KernelCache kc16[4];
     if (G == 2 && KPS == 2)
         return plan_and_launch(nce_stats_kernel<2, 1, 16, 2, 0>, kc16[2], 128 + 16 * 32, smem, 2, mgroups, per_slice, num_tiles,
-                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
+                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill, true);
     if (G == 2 && p.epi_warps == 16)
         return plan_and_launch(nce_stats_kernel<2, 1, 16, 1, 0>, kc16[0], 128 + 16 * 32, smem, 2, mgroups, per_slice, num_tiles,
-                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
+                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill, true);
     if (G == 2)
         return plan_and_launch(nce_stats_kernel<2, 1, 8, 1, 0>, kc[0], 128 + 8 * 32, smem, 2, mgroups, per_slice, num_tiles,
-                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
+                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill, true);
     if (CS == 4)
         return plan_and_launch(nce_stats_kernel<1, 4, 8, 1, 0>, kc[1], 128 + 8 * 32, smem, 4, mgroups, per_slice, num_tiles,
-                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
+                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill, true);
     if (CS == 2)
         return plan_and_launch(nce_stats_kernel<1, 2, 8, 1, 0>, kc[2], 128 + 8 * 32, smem, 2, mgroups, per_slice, num_tiles,
-                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
+                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill, true);
     static KernelCache kc_dense;
     if (p.epi_warps == 16 && p.logits != nullptr)
         return plan_and_launch(nce_stats_kernel<1, 1, 16, 1, 1>, kc_dense, 128 + 16 * 32, smem, 1, mgroups, per_slice,
-                               num_tiles, n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
+                               num_tiles, n_pad, &p.slices, stream, tm_q, tm_queue, a, fill, true);
     if (p.epi_warps == 16)
         return plan_and_launch(nce_stats_kernel<1, 1, 16, 1, 0>, kc16[1], 128 + 16 * 32, smem, 1, mgroups, per_slice, num_tiles,
-                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill);
+                               n_pad, &p.slices, stream, tm_q, tm_queue, a, fill, true);
     return plan_and_launch(nce_stats_kernel<1, 1, 8, 1, 0>, kc[3], 128 + 8 * 32, smem, 1, mgroups, per_slice, num_tiles, n_pad,
-                           &p.slices, stream, tm_q, tm_queue, a, fill);
+                           &p.slices, stream, tm_q, tm_queue, a, fill, true);
 }
 
 cudaError_t launch_nce_dq_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* queue, int N, int C, int K,

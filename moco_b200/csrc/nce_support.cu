@@ -66,6 +66,8 @@ __device__ void finish_mean(unsigned int* counter, int N, const float* loss_rows
 __global__ void prep_kernel(const void* __restrict__ q, const void* __restrict__ k, int dtype, int N, int C,
                             float* __restrict__ lpos, __nv_bfloat16* __restrict__ q_bf16,
                             unsigned int* __restrict__ counters) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x < 4) counters[threadIdx.x] = 0u;
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= N) return;
@@ -85,9 +87,8 @@ __global__ void prep_kernel(const void* __restrict__ q, const void* __restrict__
 cudaError_t launch_prep(const void* q, const void* k, int qk_dtype, int N, int C, const NceWorkspace& ws,
                         cudaStream_t stream) {
     int rows_per_block = 4;
-    prep_kernel<<<(N + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, stream>>>(
-        q, k, qk_dtype, N, C, ws.lpos, ws.q_bf16, ws.counters);
-    return cudaGetLastError();
+    return launch_pdl(prep_kernel, dim3((N + rows_per_block - 1) / rows_per_block), dim3(rows_per_block * 32), 0, stream,
+                      q, k, qk_dtype, N, C, ws.lpos, ws.q_bf16, ws.counters);
 }
 
 // ---------------------------------------------------------------------------
@@ -100,6 +101,8 @@ __global__ void combine_kernel(int N, int C, int K, int slices, int n_pad, float
                                float* __restrict__ lse, float* __restrict__ loss_rows,
                                float* __restrict__ prob_rows, float* __restrict__ loss_prob,
                                unsigned int* __restrict__ counters, float2* __restrict__ ms_out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp per q row
     const float scale2 = inv_T * kLog2e;
     if (ms_out != nullptr) {
@@ -150,10 +153,9 @@ cudaError_t launch_combine(int N, int C, int slices, int n_pad, float inv_T, flo
                            float* loss_rows, float* prob_rows, float* loss_prob, const NceWorkspace& ws,
                            cudaStream_t stream) {
     const int rows_per_block = 8;
-    combine_kernel<<<(N + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, stream>>>(
-        N, C, K, slices, n_pad, inv_T, ws.lpos, ws.part_ms, logits, lse, loss_rows, prob_rows, loss_prob, ws.counters,
-        nullptr);
-    return cudaGetLastError();
+    return launch_pdl(combine_kernel, dim3((N + rows_per_block - 1) / rows_per_block), dim3(rows_per_block * 32), 0,
+                      stream, N, C, K, slices, n_pad, inv_T, ws.lpos, ws.part_ms, logits, lse, loss_rows, prob_rows,
+                      loss_prob, ws.counters, nullptr);
 }
 
 // sharded queue, step 1: this rank's slices -> ms_out[N]
@@ -184,6 +186,8 @@ __global__ void dq_reduce_kernel(int N, int C, int slices, int n_pad, float inv_
     // 256 threads = (C/4 float4 lanes) x groups; group g sums slices g, g+groups, ...; groups are then
     // added in index order (deterministic).
     __shared__ float4 s_part[256];
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x;
     const int lanes = C >> 2;
     const int groups = 256 / lanes;
@@ -229,8 +233,8 @@ cudaError_t launch_dq_reduce(int N, int C, int slices, int n_pad, float inv_T, c
                              const float* prob_rows, float* dq, const float* part_o, cudaStream_t stream,
                              const float2* part_ms, const float* lse) {
     if ((C & 3) != 0 || C > 1024) return cudaErrorNotSupported;
-    dq_reduce_kernel<<<N, 256, 0, stream>>>(N, C, slices, n_pad, inv_T, k, k_dtype, part_o, prob_rows, dq, part_ms, lse);
-    return cudaGetLastError();
+    return launch_pdl(dq_reduce_kernel, dim3(N), dim3(256), 0, stream, N, C, slices, n_pad, inv_T, k, k_dtype, part_o,
+                      prob_rows, dq, part_ms, lse);
 }
 
 // ---------------------------------------------------------------------------

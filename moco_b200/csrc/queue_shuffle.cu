@@ -13,6 +13,8 @@ namespace moco {
 __global__ void enqueue_kernel(__nv_bfloat16* __restrict__ qb, float* __restrict__ qf,
                                const void* __restrict__ k_all, int k_dtype, int n_all, int C, long long K,
                                long long index, long long row0, long long nrows) {
+    pdl_launch_dependents();
+    pdl_wait();                  // the kernels that read the pre-enqueue queue (this step's head) are complete
     const int vec_per_row = C >> 3;
     const long long total = (long long)n_all * vec_per_row;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -48,6 +50,8 @@ __global__ void enqueue_kernel(__nv_bfloat16* __restrict__ qb, float* __restrict
 __global__ void enqueue_scalar_kernel(__nv_bfloat16* __restrict__ qb, float* __restrict__ qf,
                                       const void* __restrict__ k_all, int k_dtype, int n_all, int C, long long K,
                                       long long index, long long row0, long long nrows) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = (long long)n_all * C;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
@@ -68,12 +72,14 @@ cudaError_t launch_enqueue(__nv_bfloat16* queue_bf16, float* queue_f32, const vo
         long long total = (long long)n_all * (C >> 3);
         int blocks = (int)((total + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        enqueue_kernel<<<blocks, 256, 0, stream>>>(queue_bf16, queue_f32, k_all, k_dtype, n_all, C, K, index, row0, nrows);
+        return launch_pdl(enqueue_kernel, dim3(blocks), dim3(256), 0, stream, queue_bf16, queue_f32, k_all, k_dtype, n_all, C,
+                          (long long)K, (long long)index, (long long)row0, (long long)nrows);
     } else {
         long long total = (long long)n_all * C;
         int blocks = (int)((total + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        enqueue_scalar_kernel<<<blocks, 256, 0, stream>>>(queue_bf16, queue_f32, k_all, k_dtype, n_all, C, K, index, row0, nrows);
+        return launch_pdl(enqueue_scalar_kernel, dim3(blocks), dim3(256), 0, stream, queue_bf16, queue_f32, k_all, k_dtype,
+                          n_all, C, (long long)K, (long long)index, (long long)row0, (long long)nrows);
     }
     return cudaGetLastError();
 }

@@ -36,6 +36,14 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
+// Programmatic dependent launch (PDL).  A kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still running: everything before pdl_wait() (barrier init, TMEM
+// allocation, descriptor prefetch -- nothing that touches global memory) overlaps the predecessor's tail;
+// pdl_wait() returns once the predecessor grid has completed and its writes are visible.  Both are no-ops for a
+// kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }

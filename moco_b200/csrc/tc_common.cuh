@@ -90,19 +90,28 @@ static cudaError_t prepare_kernel(Kern kern, KernelCache& kc, int threads, int s
 
 template <typename Kern, typename Args>
 static cudaError_t launch_cluster(Kern kern, int grid, int threads, int smem, int cluster, cudaStream_t stream,
-                                  const CUtensorMap& a, const CUtensorMap& b, const Args& args) {
+                                  const CUtensorMap& a, const CUtensorMap& b, const Args& args, bool pdl = false) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster > 1) {                          // plain launch when no cluster feature is used
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl && pdl_enabled()) {                 // only for kernels that call pdl_wait() (common.cuh)
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = (cluster > 1) ? 1 : 0;      // plain launch when no cluster feature is used
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kern, a, b, args);
 }
 
@@ -110,7 +119,7 @@ static cudaError_t launch_cluster(Kern kern, int grid, int threads, int smem, in
 template <typename Kern, typename Args, typename Fill>
 static cudaError_t plan_and_launch(Kern kern, KernelCache& kc, int threads, int smem, int cluster, int mgroups,
                                    int ctas_per_slice, int num_tiles, int n_pad, int* slices_out, cudaStream_t stream,
-                                   const CUtensorMap& a, const CUtensorMap& b, Args& args, Fill fill) {
+                                   const CUtensorMap& a, const CUtensorMap& b, Args& args, Fill fill, bool pdl = false) {
     int max_clusters = 0;
     cudaError_t e = prepare_kernel(kern, kc, threads, smem, cluster, &max_clusters);
     if (e != cudaSuccess) return e;
@@ -121,7 +130,7 @@ static cudaError_t plan_and_launch(Kern kern, KernelCache& kc, int threads, int 
     if (slices < 1) return cudaErrorNotSupported;
     *slices_out = slices;
     fill(args, slices);
-    return launch_cluster(kern, ctas_per_slice * slices, threads, smem, cluster, stream, a, b, args);
+    return launch_cluster(kern, ctas_per_slice * slices, threads, smem, cluster, stream, a, b, args, pdl);
 }
 
 // largest multicast cluster size in {4, 2, 1} that divides the number of q row blocks
