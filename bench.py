@@ -222,7 +222,8 @@ def run_native(args):
     opt = torch.optim.SGD(model.parameters(), lr=0.03 * N * world / 256, momentum=0.9, weight_decay=1e-4)
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False)
-    step = MoCoStep(model, model_ema, contrast, opt)
+    nhwc = args.memory_format == "channels_last"
+    step = MoCoStep(model, model_ema, contrast, opt, channels_last=nhwc)
 
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     dev_inputs = torch.randn(N, 6, 224, 224, device=dev, generator=gen)           # dataset.py:31-33 layout
@@ -230,7 +231,9 @@ def run_native(args):
     epoch = 1
 
     def split(t):
-        x1, x2 = torch.split(t, [3, 3], dim=1)
+        x1, x2 = torch.split(t, [3, 3], dim=1)                       # train.py:250 (views of the 6-channel batch)
+        if nhwc:
+            return x1, x2                 # MoCoStep reads the crops in place (moco_crop_to_nhwc_bf16)
         return (x1.contiguous(memory_format=mf), x2.contiguous())
 
     def barrier():

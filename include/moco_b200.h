@@ -189,6 +189,22 @@ int moco_ema_update(const void* segs_dev, const int32_t* chunk_prefix_dev, int n
                     float m, float one_minus_m, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Input path: one crop of the [N, C_total, H, W] batch ->
+ * bf16 [N, H, W, C] (channels_last storage) in ONE pass.  Replaces the crop
+ * split of train.py:250-254 (`torch.split(inputs, [3, 3], dim=1)` + the
+ * discarded `.contiguous()` calls) and the cast + layout passes mixed
+ * precision / cuDNN put in front of the first convolution.
+ *
+ * src: MOCO_F32 or MOCO_BF16, NCHW, pointing at the crop's first channel of
+ * image 0; `src_image_stride` = ELEMENTS between consecutive images (C_total *
+ * H*W, so a crop is read in place from the 6-channel batch).  dst: dense
+ * [N, H*W, C] bf16.  C <= 4, H*W a multiple of 8, src 16-byte aligned.
+ * Values are rounded to nearest-even bf16 -- bit-identical to torch's
+ * `.to(torch.bfloat16)`. */
+int moco_crop_to_nhwc_bf16(const void* src, int src_dtype, long long src_image_stride, void* dst_bf16,
+                           int N, int C, int HW, void* stream);
+
+/* ------------------------------------------------------------------------
  * ShuffleBN row gather over NVLink peer memory.  Replaces dist_collect +
  * fancy-index (moco/util.py:47-58,74-79,88-91): instead of all_gather-ing every
  * rank's batch and indexing, each rank pulls exactly the rows it needs.

@@ -342,6 +342,22 @@ int moco_ema_update(const void* segs, const int32_t* chunk_prefix, int n_segs, i
     return MOCO_OK;
 }
 
+int moco_crop_to_nhwc_bf16(const void* src, int src_dtype, long long src_image_stride, void* dst, int N, int C, int HW,
+                           void* stream_) {
+    g_err[0] = 0;
+    if (N < 0 || !dst || (!src && N) || (src_dtype != MOCO_F32 && src_dtype != MOCO_BF16) || src_image_stride < (long long)C * HW ||
+        (reinterpret_cast<uintptr_t>(src) & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0 ||
+        (src_image_stride & (src_dtype == MOCO_F32 ? 3 : 7)) != 0) {
+        set_error("moco_crop_to_nhwc_bf16: bad argument");
+        return MOCO_ERR_INVALID;
+    }
+    cudaError_t e = launch_crop_to_nhwc(src, src_dtype, src_image_stride, static_cast<__nv_bfloat16*>(dst), N, C, HW,
+                                        static_cast<cudaStream_t>(stream_));
+    if (e == cudaErrorNotSupported) { set_error("moco_crop_to_nhwc_bf16: needs C <= 4 and H*W %% 8 == 0 (C=%d HW=%d)", C, HW); return MOCO_ERR_UNSUPPORTED; }
+    if (e != cudaSuccess) return cuda_fail("crop->nhwc kernel", e);
+    return MOCO_OK;
+}
+
 int moco_shuffle_gather(const void* const* peers, int world, int rows_per_rank, const int64_t* src_rows, int n_rows,
                         size_t row_bytes, void* dst, int flags, void* stream_) {
     g_err[0] = 0;

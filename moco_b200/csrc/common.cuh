@@ -90,6 +90,8 @@ cudaError_t launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, c
 int ema_chunk_elems();
 cudaError_t launch_ema(const void* segs, const int* chunk_prefix, int n_segs, int n_chunks, float m,
                        float one_minus_m, cudaStream_t stream);
+cudaError_t launch_crop_to_nhwc(const void* src, int src_dtype, long long img_stride, __nv_bfloat16* dst, int N, int C,
+                                int HW, cudaStream_t stream);
 cudaError_t launch_gather(const void* const* peers, int world, int rows_per_rank, const int64_t* src_rows,
                           int n_rows, size_t row_bytes, void* dst, int flags, cudaStream_t stream);
 cudaError_t launch_signal_barrier(void* const* pads, int world, int rank, uint32_t epoch, cudaStream_t stream);

@@ -267,3 +267,72 @@ cudaError_t launch_signal_barrier(void* const* pads_host, int world, int rank, u
 }
 
 }  // namespace moco
+
+// ---------------------------------------------------------------------------
+// Input path: one crop of the NCHW batch -> bf16 NHWC (channels_last storage), one pass.
+// Reference: train.py:250-254 splits the 6-channel batch into two crops; Apex/autocast then casts to half and
+// cuDNN converts the layout in front of the first convolution (two more passes over the images).  Here the crop
+// selection (strided read), the cast and the layout change are one kernel; its output is what the ShuffleBN
+// gather publishes / pulls, so the key encoder's first conv reads exactly what crossed NVLink.
+// Each thread converts 8 consecutive pixels: C plane reads of 32 B, one contiguous 16*C-byte store.
+// ---------------------------------------------------------------------------
+namespace moco {
+
+template <int C, typename SrcT>
+__global__ void __launch_bounds__(256)
+crop_to_nhwc_kernel(const SrcT* __restrict__ src, long long img_stride, __nv_bfloat16* __restrict__ dst, int N, int HW) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int groups = HW >> 3;                                   // 8-pixel groups per image
+    const long long total = (long long)N * groups;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(t / groups), gidx = (int)(t % groups);
+        const SrcT* s = src + (size_t)n * img_stride + (size_t)gidx * 8;
+        float v[C][8];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if constexpr (sizeof(SrcT) == 4) {
+                const float4 a = *reinterpret_cast<const float4*>(s + (size_t)c * HW);
+                const float4 b = *reinterpret_cast<const float4*>(s + (size_t)c * HW + 4);
+                v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
+                v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+            } else {
+                const uint4 u = *reinterpret_cast<const uint4*>(s + (size_t)c * HW);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h[e]); v[c][2 * e] = f.x; v[c][2 * e + 1] = f.y; }
+            }
+        }
+        // interleave: out[p * C + c]
+        __align__(16) __nv_bfloat16 o[8 * C];
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+#pragma unroll
+            for (int c = 0; c < C; ++c) o[p * C + c] = __float2bfloat16_rn(v[c][p]);
+        uint4* d = reinterpret_cast<uint4*>(dst + ((size_t)n * HW + (size_t)gidx * 8) * C);
+#pragma unroll
+        for (int w = 0; w < C; ++w) d[w] = reinterpret_cast<const uint4*>(o)[w];        // 8*C bf16 = C x 16 bytes
+    }
+}
+
+cudaError_t launch_crop_to_nhwc(const void* src, int src_dtype, long long img_stride, __nv_bfloat16* dst, int N, int C,
+                                int HW, cudaStream_t stream) {
+    if (N == 0) return cudaSuccess;
+    if (C < 1 || C > 4 || (HW & 7) != 0) return cudaErrorNotSupported;
+    const long long total = (long long)N * (HW >> 3);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+#define MOCO_CROP(C_)                                                                                                 \
+    if (C == C_) {                                                                                                    \
+        if (src_dtype == 0)                                                                                           \
+            return launch_pdl(crop_to_nhwc_kernel<C_, float>, dim3((unsigned)blocks), dim3(256), 0, stream,            \
+                              static_cast<const float*>(src), img_stride, dst, N, HW);                                \
+        return launch_pdl(crop_to_nhwc_kernel<C_, __nv_bfloat16>, dim3((unsigned)blocks), dim3(256), 0, stream,        \
+                          static_cast<const __nv_bfloat16*>(src), img_stride, dst, N, HW);                            \
+    }
+    MOCO_CROP(1) MOCO_CROP(2) MOCO_CROP(3) MOCO_CROP(4)
+#undef MOCO_CROP
+    return cudaErrorNotSupported;
+}
+
+}  // namespace moco

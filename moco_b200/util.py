@@ -115,6 +115,7 @@ class ShuffleContext:
         self.staging: Dict[str, list] = {}
         self.turn: Dict[str, int] = {}
         self.gather_flags = _lib.GATHER_AUTO
+        self._local_stage: Dict[str, torch.Tensor] = {}
 
     @classmethod
     def get(cls) -> "ShuffleContext":
@@ -141,14 +142,22 @@ class ShuffleContext:
         _lib.check(lib.moco_signal_barrier(self.pad.table, self.world, self.rank, self.epoch, _lib.cur_stream()),
                    "moco_signal_barrier")
 
-    def gather(self, kind: str, x: torch.Tensor, src_rows: torch.Tensor, cast_dtype=None) -> torch.Tensor:
+    def gather(self, kind: str, x: torch.Tensor, src_rows: torch.Tensor, cast_dtype=None,
+               channels_last: bool = False) -> torch.Tensor:
         """out[i] = (rank-major concatenation of every rank's x)[src_rows[i]].
 
         cast_dtype (world > 1 only): publish the batch in this dtype -- the cast is fused into the copy
         into the peer-visible staging buffer, so e.g. fp32 images cross NVLink as bf16 (what the autocast
-        key encoder would round them to anyway)."""
+        key encoder would round them to anyway).
+
+        channels_last (images): publish the batch as bf16 NHWC with ONE kernel
+        (``moco_crop_to_nhwc_bf16``: crop selection from a wider NCHW batch, cast and layout change together) and
+        return a bf16 ``channels_last`` tensor, so the first convolution of a channels_last encoder reads exactly
+        the bytes that were gathered -- no ``.contiguous()``, cast or layout pass in between."""
         lib = _lib.load()
         _lib.require_cuda(x, src_rows)
+        if channels_last:
+            return self._gather_nhwc(kind, x, src_rows)
         x = x.contiguous()
         n = x.shape[0]
         dtype = cast_dtype if (cast_dtype is not None and self.world > 1) else x.dtype
@@ -171,6 +180,61 @@ class ShuffleContext:
                    "moco_shuffle_gather")
         return out
 
+    def _gather_nhwc(self, kind: str, x: torch.Tensor, src_rows: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        if x.dim() != 4:
+            raise ValueError("moco_b200 shuffle: channels_last needs an [N, C, H, W] batch")
+        n, C, H, W = x.shape
+        _check_nhwc_shape(C, H, W)
+        if n and x.stride()[1:] != (H * W, W, 1):          # a channel slice of a wider NCHW batch is read in place
+            x = x.contiguous()
+        img_stride = x.stride(0) if n else C * H * W
+        row_bytes = C * H * W * 2
+        if row_bytes % 16 != 0:
+            raise ValueError(f"moco_b200 shuffle: row size {row_bytes} B is not a multiple of 16")
+        if self.world == 1:                                 # private staging (no peers to publish to)
+            st = self._local_stage.get(kind)
+            if st is None or st.numel() < n * row_bytes:
+                st = self._local_stage[kind] = torch.empty(max(n * row_bytes, 16), dtype=torch.uint8, device=x.device)
+            stage_ptr, table = st.data_ptr(), (ctypes.c_void_p * 1)(st.data_ptr())
+        else:
+            buf = self._staging(kind + "_nhwc", n * row_bytes)
+            stage_ptr, table = buf.local, buf.table
+        _lib.check(lib.moco_crop_to_nhwc_bf16(x.data_ptr(), _lib.dtype_code(x), img_stride, stage_ptr, n, C, H * W,
+                                              _lib.cur_stream()), "moco_crop_to_nhwc_bf16")
+        if self.world > 1:
+            self.barrier()
+        out = torch.empty((src_rows.shape[0], C, H, W), dtype=torch.bfloat16, device=x.device,
+                          memory_format=torch.channels_last)
+        _lib.check(lib.moco_shuffle_gather(table, self.world, n, src_rows.data_ptr(), src_rows.shape[0],
+                                           row_bytes, out.data_ptr(), self.gather_flags, _lib.cur_stream()),
+                   "moco_shuffle_gather")
+        return out
+
+
+def _check_nhwc_shape(C: int, H: int, W: int) -> None:
+    if C > 4 or (H * W) % 8 != 0:
+        raise ValueError(f"moco_b200: the fused bf16/NHWC image path needs C <= 4 and H*W % 8 == 0 (got C={C}, H*W={H * W})")
+
+
+def crop_to_channels_last_bf16(x: torch.Tensor) -> torch.Tensor:
+    """[N, C, H, W] fp32/bf16 (possibly a channel slice of a wider NCHW batch, e.g. one crop of the reference's
+    6-channel input, train.py:250) -> bf16 tensor of the same shape in ``channels_last`` storage, one kernel
+    (``moco_crop_to_nhwc_bf16``).  Bit-identical to ``x.to(torch.bfloat16).contiguous(memory_format=channels_last)``."""
+    lib = _lib.load()
+    _lib.require_cuda(x)
+    if x.dim() != 4:
+        raise ValueError("crop_to_channels_last_bf16: expected [N, C, H, W]")
+    n, C, H, W = x.shape
+    _check_nhwc_shape(C, H, W)
+    if n and x.stride()[1:] != (H * W, W, 1):
+        x = x.contiguous()
+    out = torch.empty((n, C, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.moco_crop_to_nhwc_bf16(x.data_ptr(), _lib.dtype_code(x), x.stride(0) if n else C * H * W,
+                                              out.data_ptr(), n, C, H * W, _lib.cur_stream()), "moco_crop_to_nhwc_bf16")
+    return out
+
 
 # ---------------------------------------------------------------------------
 # reference API
@@ -188,14 +252,14 @@ def dist_collect(x):
 
 class DistributedShufle:
     @staticmethod
-    def forward_shuffle(x, epoch, cast_dtype=None):
+    def forward_shuffle(x, epoch, cast_dtype=None, channels_last=False):
         """forward shuffle, return shuffled batch of x from all processes (util.py:69-79).
         epoch is used as manual seed to make sure the shuffle id in all process is same.
-        cast_dtype: optional extension, see ShuffleContext.gather."""
+        cast_dtype / channels_last: optional extensions, see ShuffleContext.gather."""
         rank, world = _world()
         forward_inds, backward_inds = DistributedShufle.get_shuffle_ids(x.shape[0] * world, epoch, x.device)
         forward_inds_local = DistributedShufle.get_local_id(forward_inds)
-        return ShuffleContext.get().gather("fwd", x, forward_inds_local, cast_dtype), backward_inds
+        return ShuffleContext.get().gather("fwd", x, forward_inds_local, cast_dtype, channels_last), backward_inds
 
     @staticmethod
     def backward_shuffle(x, backward_inds, return_local=True):

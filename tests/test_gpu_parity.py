@@ -572,3 +572,76 @@ def test_moment_update_channels_last_parameters():
     mixed = encoders.resnet18(low_dim=128).cuda()                 # NCHW vs NHWC strides differ: must refuse
     with pytest.raises(RuntimeError, match="equal strides"):
         moment_update(mixed, ema, 0.999)
+
+
+# ------------------------------------------------------------------ input path
+@pytest.mark.gpu
+@pytest.mark.parametrize("src_dtype", [torch.float32, torch.bfloat16])
+def test_crop_to_channels_last_bf16_bit_exact(src_dtype):
+    """One kernel = crop selection + cast + NCHW->NHWC; bit-identical to torch's cast + layout change."""
+    from moco_b200.util import crop_to_channels_last_bf16
+    g = torch.Generator(device="cuda").manual_seed(9)
+    six = torch.randn(5, 6, 24, 20, device="cuda", generator=g).to(src_dtype)          # H*W = 480, multiple of 8
+    for sl in (slice(0, 3), slice(3, 6), slice(2, 3), slice(1, 5)):
+        x = six[:, sl]                                                                  # a view: read in place
+        got = crop_to_channels_last_bf16(x)
+        want = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        assert got.shape == x.shape and got.dtype == torch.bfloat16
+        assert got.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(got.contiguous().view(torch.int16), want.contiguous().view(torch.int16))
+    full = torch.randn(3, 3, 224, 224, device="cuda", generator=g)
+    assert torch.equal(crop_to_channels_last_bf16(full),
+                       full.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+    with pytest.raises(ValueError, match="H\\*W"):
+        crop_to_channels_last_bf16(torch.randn(2, 3, 5, 5, device="cuda"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        crop_to_channels_last_bf16(torch.randn(2, 3, 8, 8))
+
+
+@pytest.mark.gpu
+def test_forward_shuffle_channels_last_matches_oracle():
+    """ShuffleBN forward permute with the fused bf16/NHWC publish (world 1): rows = oracle's permutation of the
+    bf16-rounded crop; output is a channels_last tensor; un-shuffle of per-row features restores the order (S6)."""
+    from moco_b200.util import DistributedShufle
+    g = torch.Generator().manual_seed(21)
+    six = torch.randn(16, 6, 16, 16, generator=g)
+    for epoch in (1, 2, 7):
+        want, bwd = O.forward_shuffle([O.bf16_round(six[:, 3:].numpy())], epoch)
+        got, binds = DistributedShufle.forward_shuffle(six.cuda()[:, 3:], epoch, channels_last=True)
+        assert got.dtype == torch.bfloat16 and got.is_contiguous(memory_format=torch.channels_last)
+        np.testing.assert_array_equal(got.float().cpu().numpy(), want[0])
+        np.testing.assert_array_equal(binds.cpu().numpy(), bwd)
+        feat = got.float().reshape(16, -1)[:, :32].contiguous()
+        _, local = DistributedShufle.backward_shuffle(feat, binds, return_local=True)
+        np.testing.assert_array_equal(local.cpu().numpy(), O.bf16_round(six[:, 3:].numpy()).reshape(16, -1)[:, :32])
+
+
+@pytest.mark.gpu
+def test_step_with_fused_input_path_matches_plain_step():
+    """MoCoStep(channels_last=True) feeds both encoders bf16 NHWC crops taken in place from the 6-channel batch; the
+    plain step lets autocast / cuDNN do the same conversions.  Same values in, same losses out."""
+    from moco_b200 import encoders
+    from moco_b200.NCE import MemoryMoCo
+    from moco_b200.train_step import MoCoStep
+    losses = []
+    for nhwc in (False, True):
+        torch.manual_seed(0)
+        model = encoders.resnet18(low_dim=128).cuda().to(memory_format=torch.channels_last)
+        ema = encoders.resnet18(low_dim=128).cuda().to(memory_format=torch.channels_last)
+        ema.load_state_dict(model.state_dict())
+        contrast = MemoryMoCo(128, 1024, 0.07).cuda()
+        opt = torch.optim.SGD(model.parameters(), lr=0.03, momentum=0.9, weight_decay=1e-4)
+        step = MoCoStep(model, ema, contrast, opt, channels_last=nhwc)
+        g = torch.Generator(device="cuda").manual_seed(4)
+        out = []
+        for _ in range(3):
+            batch = torch.randn(16, 6, 64, 64, device="cuda", generator=g)
+            x1, x2 = torch.split(batch, [3, 3], dim=1)
+            if not nhwc:
+                x1, x2 = x1.contiguous(memory_format=torch.channels_last), x2.contiguous()
+            loss, prob = step(x1, x2, 1)
+            out.append((float(loss), float(prob)))
+        losses.append(out)
+    for (l0, p0), (l1, p1) in zip(*losses):
+        assert abs(l0 - l1) < 2e-3 * max(1.0, abs(l0)), (losses)
+        assert abs(p0 - p1) < 2e-3 * max(p0, 1e-6) + 1e-6

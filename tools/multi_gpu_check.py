@@ -45,6 +45,16 @@ def main():
         ok = ok and np.array_equal(g_loc.cpu().numpy(), xs[rank].numpy().reshape(n, -1)[:, :32])
         res[f"iter{it}"] = bool(ok)
         res["ok"] = res["ok"] and bool(ok)
+    # fused input path: crops of a 6-channel batch published as bf16 NHWC, twice (double buffering)
+    for it, epoch in enumerate([3, 4]):
+        six = [batch(r, 8, (6, 8, 8), 50 + it) for r in range(world)]
+        crops = [O.bf16_round(x[:, 3:].numpy()) for x in six]                              # second crop, bf16 values
+        outs, _ = O.forward_shuffle(crops, epoch)
+        mine, _ = DistributedShufle.forward_shuffle(six[rank].to(dev)[:, 3:], epoch, channels_last=True)
+        ok = (mine.dtype == torch.bfloat16 and mine.is_contiguous(memory_format=torch.channels_last)
+              and np.array_equal(mine.float().cpu().numpy(), outs[rank]))
+        res[f"nhwc{it}"] = bool(ok)
+        res["ok"] = res["ok"] and bool(ok)
     col = dist_collect(xs[rank].to(dev))
     ok = np.array_equal(col.cpu().numpy(), O.dist_collect([x.numpy() for x in xs]))
     res["dist_collect"] = bool(ok)
