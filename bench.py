@@ -47,7 +47,7 @@ def parse():
 # `ncu --set full` captures (profiles/r1_final_nce_c2_ncu_metrics.csv, profiles/r1_final_nce_c5_ncu_metrics.csv)
 NCU_TRAFFIC_BYTES = {(256, 128, 16384): 4287232, (512, 256, 262144): 134522880 + 3844352,   # statistics kernel
                      # one-pass kernel (profiles/r1_onepass_c2_ncu_metrics.csv, r1_onepass_c5_ncu_metrics.csv)
-                     ("onepass", 256, 128, 16384): 4306176, ("onepass", 512, 256, 262144): 134687232 + 5179392}
+                     ("onepass", 256, 128, 16384): 4308992, ("onepass", 512, 256, 262144): 134518528 + 3464192}
 
 
 def load_peaks():
