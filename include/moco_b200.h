@@ -146,6 +146,13 @@ int moco_queue_enqueue(void* queue_bf16, float* queue_f32_or_null,
  *   ... reduce_scatter o_partial -> o_own [N, C] ...
  *   moco_nce_shard_dq_finish : dq_i = inv_T / N * (o_own_i + (prob_i - 1) * k_i)
  *
+ * With MOCO_NCE_ONE_PASS in `flags` of BOTH moco_nce_shard_stats and
+ * moco_nce_shard_dq, the statistics call makes the only sweep over the shard
+ * (it also leaves the unnormalised P~.Queue partials in the workspace) and the
+ * dq call just rescales and sums them with the merged lse -- the caller must not
+ * use the workspace for anything else in between (moco_nce_shard_merge is fine).
+ * Same numerical contract as MOCO_NCE_ONE_PASS of moco_nce_fwd.
+ *
  * The loss is permutation-invariant over negatives, so it equals the replicated
  * reference's; ring slot g of moco/NCE/Contrast.py:32 maps to (rank g / (K/W),
  * local row g % (K/W)) -- moco_queue_enqueue_shard writes only the slots this

@@ -51,8 +51,16 @@ class _ShardedNCE(torch.autograd.Function):
         stream = _lib.cur_stream()
         inv_T = 1.0 / mod.temperature
         ms = torch.empty(Nq, 2, **f32)
+        # loss statistics AND the unnormalised gradient partials from one sweep over the shard when a gradient is
+        # wanted and the temperature allows it (same policy as moco_nce_fwd, include/moco_b200.h)
+        flags = mod.kernel_flags
+        if (q.requires_grad and not (flags & (_lib.NCE_TWO_PASS | _lib.NCE_DQ_V1 | _lib.NCE_ONE_PASS))
+                and inv_T <= _lib.ONE_PASS_MAX_INV_T):
+            flags |= _lib.NCE_ONE_PASS
+        if not q.requires_grad:
+            flags &= ~_lib.NCE_ONE_PASS
         _lib.check(lib.moco_nce_shard_stats(q_all.data_ptr(), k_all.data_ptr(), dt, shard.data_ptr(), Nq, C, Ks, inv_T,
-                                            ms.data_ptr(), ws_ptr, ws_bytes, mod.kernel_flags, stream),
+                                            ms.data_ptr(), ws_ptr, ws_bytes, flags, stream),
                    "moco_nce_shard_stats")
         if world > 1:
             ms_all = torch.empty(world, Nq, 2, **f32)
@@ -71,7 +79,7 @@ class _ShardedNCE(torch.autograd.Function):
         if q.requires_grad:
             o_part = torch.empty(Nq, C, **f32)
             _lib.check(lib.moco_nce_shard_dq(q_all.data_ptr(), dt, shard.data_ptr(), lse.data_ptr(), Nq, C, Ks, inv_T,
-                                             o_part.data_ptr(), ws_ptr, ws_bytes, mod.kernel_flags, stream),
+                                             o_part.data_ptr(), ws_ptr, ws_bytes, flags, stream),
                        "moco_nce_shard_dq")
             if world > 1:
                 o_own = torch.empty(N, C, **f32)

@@ -102,6 +102,8 @@ class _Counting:
             fn = getattr(lib, name)
             if name == "moco_nce_fwd":
                 setattr(self, name, self._wrap_nce(fn))
+            elif name == "moco_nce_shard_dq":      # one-pass finish: dq_reduce only; two-pass: dq kernel + dq_reduce
+                setattr(self, name, self._wrap_flags(fn, 11))
             elif name in self._PER_CALL:
                 setattr(self, name, self._wrap(fn, self._PER_CALL[name]))
             else:
@@ -114,6 +116,16 @@ class _Counting:
             rc = fn(*a)
             if rc == 0:
                 launches += n
+            return rc
+        return call
+
+    @staticmethod
+    def _wrap_flags(fn, flag_index):
+        def call(*a):
+            global launches
+            rc = fn(*a)
+            if rc == 0:
+                launches += 1 if (a[flag_index] & NCE_ONE_PASS) else 2
             return rc
         return call
 

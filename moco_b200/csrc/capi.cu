@@ -261,8 +261,15 @@ int moco_nce_shard_stats(const void* q_all, const void* k_all, int qk_dtype, con
     p.epi_warps = (flags & MOCO_NCE_EPI8) ? 8 : 16;
     p.kps1 = (flags & MOCO_NCE_KPS1) ? 1 : 0;
     p.slices = 0; p.n_pad = 0;
-    e = (flags & MOCO_NCE_STATS_TS) ? launch_nce_stats3(p, p.epi_warps, ws, stream) : launch_nce_tc(p, ws, stream);
-    if (e != cudaSuccess) return cuda_fail("tcgen05 stats kernel", e);
+    if (flags & MOCO_NCE_ONE_PASS) {
+        // one sweep over the shard: (stabiliser, sum) partials for the cross-rank merge AND the unnormalised
+        // P~.Queue partials, which stay in the workspace until moco_nce_shard_dq(..., MOCO_NCE_ONE_PASS) rescales them
+        e = launch_nce_dq2_tc(p.q_bf16, p.queue, N, C, Ks, inv_T, nullptr, d.sms, p.max_share, &p.slices, &p.n_pad, ws, stream);
+        if (e != cudaSuccess) return cuda_fail("tcgen05 one-pass kernel", e);
+    } else {
+        e = (flags & MOCO_NCE_STATS_TS) ? launch_nce_stats3(p, p.epi_warps, ws, stream) : launch_nce_tc(p, ws, stream);
+        if (e != cudaSuccess) return cuda_fail("tcgen05 stats kernel", e);
+    }
     e = launch_combine_partial(N, p.slices, p.n_pad, static_cast<float2*>(ms_out), ws, stream);
     if (e != cudaSuccess) return cuda_fail("combine kernel", e);
     return MOCO_OK;
@@ -297,6 +304,16 @@ int moco_nce_shard_dq(const void* q_all, int q_dtype, const void* shard_bf16, co
     const int max_share = (flags & MOCO_NCE_SHARE4) ? 4 : ((flags & MOCO_NCE_SHARE2) ? 2 : 1);
     int slices = 0, n_pad = 0;
     cudaError_t e;
+    if (flags & MOCO_NCE_ONE_PASS) {
+        // the sweep already happened in moco_nce_shard_stats(..., MOCO_NCE_ONE_PASS) on this workspace: only the
+        // slice count is needed, then O = sum_s 2^(m_s - lse) O~_s
+        e = launch_nce_dq2_tc(qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, nullptr, d.sms, max_share,
+                              &slices, &n_pad, ws, stream, /*plan_only=*/true);
+        if (e != cudaSuccess) return cuda_fail("one-pass plan", e);
+        e = launch_dq_reduce(N, C, slices, n_pad, inv_T, nullptr, 0, nullptr, o_partial, ws.part_o, stream, ws.part_ms, lse_all);
+        if (e != cudaSuccess) return cuda_fail("dq reduce kernel", e);
+        return MOCO_OK;
+    }
     if (flags & MOCO_NCE_DQ_V1)
         e = launch_nce_dq_tc(qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, lse_all, d.sms, max_share, &slices, &n_pad, ws, stream);
     else

@@ -116,7 +116,7 @@ cudaError_t launch_nce_tc(NceTcParams& p, const NceWorkspace& ws, cudaStream_t s
 cudaError_t launch_nce_stats3(NceTcParams& p, int epi_warps, const NceWorkspace& ws, cudaStream_t stream);
 cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* queue, int N, int C, int K,
                               float inv_T, const float* lse, int num_sms, int max_share, int* slices_out,
-                              int* n_pad_out, const NceWorkspace& ws, cudaStream_t stream);
+                              int* n_pad_out, const NceWorkspace& ws, cudaStream_t stream, bool plan_only = false);
 cudaError_t launch_nce_dq_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* queue, int N, int C, int K,
                              float inv_T, const float* lse, int num_sms, int max_share, int* slices_out, int* n_pad_out,
                              const NceWorkspace& ws, cudaStream_t stream);

@@ -458,10 +458,11 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
     if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
-// lse == nullptr selects the one-pass mode: the kernel also writes ws.part_ms (see the header comment)
+// lse == nullptr selects the one-pass mode: the kernel also writes ws.part_ms (see the header comment).
+// plan_only: launch nothing, just report the slice count / padded rows this shape gets (sharded one-pass finish).
 cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* queue, int N, int C, int K,
                               float inv_T, const float* lse, int num_sms, int max_share, int* slices_out,
-                              int* n_pad_out, const NceWorkspace& ws, cudaStream_t stream) {
+                              int* n_pad_out, const NceWorkspace& ws, cudaStream_t stream, bool plan_only) {
     const bool fused = (lse == nullptr);
     if (C % 64 != 0 || C < 64 || C > 256) return cudaErrorNotSupported;
     const int kchunks = C / 64;
@@ -499,9 +500,10 @@ cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* 
         if (fused)                                                                                                 \
             return plan_and_launch(nce_dq2_kernel<CS_, BN_, true, kIss2>, kc[6 + IDX], kDq2Threads, smem, CS_,     \
                                    mgroups, mblks, num_tiles, n_pad, slices_out, stream, tm_queue, tm_queue, a,    \
-                                   fill, true);                                                                    \
+                                   fill, true, plan_only);                                                         \
         return plan_and_launch(nce_dq2_kernel<CS_, BN_, false, kIss2>, kc[IDX], kDq2Threads, smem, CS_, mgroups,   \
-                               mblks, num_tiles, n_pad, slices_out, stream, tm_queue, tm_queue, a, fill, true);    \
+                               mblks, num_tiles, n_pad, slices_out, stream, tm_queue, tm_queue, a, fill, true,     \
+                               plan_only);                                                                         \
     } while (0)
     if (BN == 128) {
         if (CS == 4) MOCO_DQ2_LAUNCH(4, 128, 0);

@@ -119,7 +119,8 @@ static cudaError_t launch_cluster(Kern kern, int grid, int threads, int smem, in
 template <typename Kern, typename Args, typename Fill>
 static cudaError_t plan_and_launch(Kern kern, KernelCache& kc, int threads, int smem, int cluster, int mgroups,
                                    int ctas_per_slice, int num_tiles, int n_pad, int* slices_out, cudaStream_t stream,
-                                   const CUtensorMap& a, const CUtensorMap& b, Args& args, Fill fill, bool pdl = false) {
+                                   const CUtensorMap& a, const CUtensorMap& b, Args& args, Fill fill, bool pdl = false,
+                                   bool plan_only = false) {
     int max_clusters = 0;
     cudaError_t e = prepare_kernel(kern, kc, threads, smem, cluster, &max_clusters);
     if (e != cudaSuccess) return e;
@@ -129,6 +130,7 @@ static cudaError_t plan_and_launch(Kern kern, KernelCache& kc, int threads, int 
     while ((size_t)slices * n_pad > (size_t)kMaxCtas * kRowsPerCta) --slices;
     if (slices < 1) return cudaErrorNotSupported;
     *slices_out = slices;
+    if (plan_only) return cudaSuccess;          // the caller only needs the (deterministic) slice count
     fill(args, slices);
     return launch_cluster(kern, ctas_per_slice * slices, threads, smem, cluster, stream, a, b, args, pdl);
 }

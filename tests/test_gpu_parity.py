@@ -338,16 +338,21 @@ def test_shufflebn_full_size_images_roundtrip(dtype):
     assert torch.equal(back, x)
 
 
-def test_sharded_queue_world1_matches_oracle():
+@pytest.mark.parametrize("mode", ["auto_one_pass", "two_pass"])
+def test_sharded_queue_world1_matches_oracle(mode):
     """ShardedMemoryMoCo at world_size 1 (one shard == the whole ring): same loss / prob / dq / FIFO as the
-    reference's replicated MemoryMoCo.  (world_size > 1: tests/test_gpu_multi.py.)"""
+    reference's replicated MemoryMoCo, with the one-sweep shard kernel (default at T = 0.07) and the two-pass
+    kernels.  (world_size > 1: tests/test_gpu_multi.py.)"""
+    from moco_b200 import _lib
     from moco_b200.NCE import ShardedMemoryMoCo
     rng = np.random.default_rng(11)
-    N, C, K, T = 64, 128, 4096, 0.07
+    N, C, K, T = 64, 128, 4096 + 77, 0.07
     mem = rand_unit(rng, K, C)
     mod = ShardedMemoryMoCo(C, K, T)
     mod.memory.copy_(torch.from_numpy(mem))
     mod = mod.cuda()
+    if mode == "two_pass":
+        mod.kernel_flags = _lib.NCE_TWO_PASS
     orc = O.MemoryMoCoOracle(mem, T)
     for _ in range(3):
         q, k = rand_unit(rng, N, C), rand_unit(rng, N, C)

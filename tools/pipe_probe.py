@@ -1,5 +1,8 @@
-"""Pipeline probe: time the stats / dq kernels with parts of the pipeline disabled (MOCO_DEBUG_MODE bits:
-1 = no epilogue math, 2 = no MMA issue, 4 = no TMA).  Results are wrong by construction; only time matters."""
+"""Pipeline probe: time a kernel with parts of its pipeline disabled (MOCO_DEBUG_MODE).  Results are wrong by
+construction; only time matters.  Today only the statistics kernel still honours bit 1 (no epilogue math); the
+one-pass/dq kernel's modes (1 = no exps, 2 = no MMA issue, 4 = no TMA) were removed after they had served
+(profiles/r1_onepass_pipeline_probe.jsonl) -- a per-element `if (debug)` was itself a 2x slowdown there.
+tools/trace_probe.py (clock64 timeline) is the tool for that kernel now."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 cases = sys.argv[1:] or ["tc1_c5", "dq2_c5"]
