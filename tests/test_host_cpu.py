@@ -233,3 +233,21 @@ def test_persist_index_roundtrip_is_reference_compatible():
     assert b.index == 0
     fresh.load_state_dict(sd)                                # reference-behaviour module ignores the value
     assert fresh.index == 0
+
+
+def test_python_flag_constants_match_the_header():
+    """moco_b200/_lib.py mirrors the MOCO_NCE_* / MOCO_GATHER_* enums and the one-pass temperature limit by hand."""
+    import re
+    from moco_b200 import _lib
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "moco_b200.h")).read()
+    enum = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(MOCO_[A-Z0-9_]+)\s*=\s*(-?\d+)", text)}
+    for name in ("AUTO", "FORCE_SIMT", "CTA_PAIR", "SINGLE_CTA", "SHARE2", "SHARE4", "DQ_V1", "STATS_TS", "EPI8", "KPS1",
+                 "TWO_PASS", "ONE_PASS"):
+        assert getattr(_lib, "NCE_" + name) == enum["MOCO_NCE_" + name], name
+    assert _lib.MOCO_F32 == enum["MOCO_F32"] and _lib.MOCO_BF16 == enum["MOCO_BF16"]
+    limit = float(re.search(r"#define\s+MOCO_ONE_PASS_MAX_INV_T\s+([0-9.]+)f", text).group(1))
+    assert _lib.ONE_PASS_MAX_INV_T == limit
+    # every flag is a distinct bit
+    bits = [enum["MOCO_NCE_" + n] for n in ("FORCE_SIMT", "CTA_PAIR", "SINGLE_CTA", "SHARE2", "SHARE4", "DQ_V1", "STATS_TS",
+                                              "EPI8", "KPS1", "TWO_PASS", "ONE_PASS")]
+    assert all(b & (b - 1) == 0 for b in bits) and len(set(bits)) == len(bits)
