@@ -290,3 +290,44 @@ def moment_update(params: Sequence[np.ndarray], params_ema: Sequence[np.ndarray]
         r = t.astype(np.float64) + np.float64(a32) * p.astype(np.float64)
         out.append(r.astype(np.float32))
     return out
+
+
+# --------------------------------------------------------------------------
+# One-sweep restatement of the head (checks the ALGORITHM of the CUDA one-pass kernel on the CPU).
+# --------------------------------------------------------------------------
+def one_sweep_head(q: np.ndarray, k: np.ndarray, memory_pre: np.ndarray, T: float, tile: int = 128,
+                   slices: int = 4) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """lse, prob and dq of the reference head (Contrast.py:20-27, NCECriterion.py:11-13, train.py:264,273)
+    computed the way ``nce_dq2_kernel<FUSED>`` does: the queue is cut into `slices` runs of `tile`-row tiles;
+    every (slice, row) keeps the row maximum of its FIRST tile as a fixed stabiliser m and accumulates
+    l = sum 2^(x - m) and O = sum 2^(x - m) queue_j in fp32 with no rescaling; slices are merged afterwards.
+    Mathematically identical to logsumexp / softmax-weighted sum; in fp32 it overflows (inf) when a later logit
+    exceeds the first tile's maximum by more than ~88 nats -- exactly the CUDA kernel's documented contract."""
+    q32, k32, mem = q.astype(np.float32), k.astype(np.float32), memory_pre.astype(np.float32)
+    N, C = q32.shape
+    K = mem.shape[0]
+    log2e = np.float32(1.4426950408889634)
+    scale2 = np.float32(1.0 / T) * log2e
+    ntiles = (K + tile - 1) // tile
+    slices = max(1, min(slices, ntiles))
+    x0 = (q32 * k32).sum(1, dtype=np.float32) * scale2                       # positive logit, log2 domain
+    parts = []
+    with np.errstate(over="ignore", invalid="ignore"):
+        for s in range(slices):
+            t0, t1 = s * ntiles // slices, (s + 1) * ntiles // slices
+            rows = mem[t0 * tile:min(t1 * tile, K)]
+            x = (q32 @ rows.T).astype(np.float32) * scale2                   # [N, rows of this slice]
+            m = x[:, :min(tile, x.shape[1])].max(1)                          # first tile only
+            p = np.exp2(x - m[:, None]).astype(np.float32)
+            parts.append((m, p.sum(1, dtype=np.float32), (p @ rows).astype(np.float32)))
+        M = np.maximum(x0, np.max([m for m, _, _ in parts], axis=0))
+        l = np.exp2(x0 - M)
+        for m, ls, _ in parts:
+            l = l + ls * np.exp2(m - M)
+        lse2 = M + np.log2(l)
+        prob = np.exp2(x0 - lse2)
+        O = np.zeros((N, C), np.float32)
+        for m, _, o in parts:
+            O += o * np.exp2(m - lse2)[:, None]
+        dq = (np.float32(1.0 / T) / np.float32(N)) * (O + (prob - 1.0)[:, None] * k32)
+    return (lse2 / log2e).astype(np.float32), prob.astype(np.float32), dq.astype(np.float32)

@@ -105,3 +105,45 @@ def test_moment_update_bit_exact(golden_dir, tag):
         ema = O.moment_update([z[f"{tag}_s{s}_p_{i}"] for i in range(n)], ema, m)
         for i, a in enumerate(ema):
             np.testing.assert_array_equal(a.view(np.uint32), z[f"{tag}_s{s}_ema_{i}"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["c1head", "wrap", "c256", "ragged"])
+def test_one_sweep_algorithm_matches_reference(contrast, name):
+    """The one-pass kernel's algorithm (fixed first-tile stabiliser, no rescaling, slice merge), restated in numpy,
+    against the reference's own lse-derived outputs and gradient on the golden inputs."""
+    g = contrast
+    N, C, K, A, steps = (int(v) for v in g[f"{name}_meta"])
+    T = float(g[f"{name}_T"][0])
+    orc = O.MemoryMoCoOracle(g[f"{name}_memory0"], T)
+    for s in range(steps):
+        q, k, k_all = g[f"{name}_s{s}_q"], g[f"{name}_s{s}_k"], g[f"{name}_s{s}_k_all"]
+        pre = orc.memory.copy()
+        for tile, slices in ((128, 4), (64, 3), (16, 7)):
+            lse, prob, dq = O.one_sweep_head(q, k, pre, T, tile=tile, slices=slices)
+            logits = g[f"{name}_s{s}_logits"]
+            ref_lse = O.logsumexp_rows(logits)
+            assert np.abs(lse - ref_lse).max() < 2e-5 * max(1.0, np.abs(ref_lse).max())
+            assert abs(float(prob.mean()) - float(g[f"{name}_s{s}_prob"][0])) < 1e-4 * float(g[f"{name}_s{s}_prob"][0]) + 1e-9
+            ref_dq = g[f"{name}_s{s}_dq"]
+            assert np.abs(dq - ref_dq).max() / np.abs(ref_dq).max() < 1e-4
+        orc.forward(q, k, k_all)
+
+
+def test_one_sweep_overflow_contract():
+    """A logit more than ~88 nats above its slice's first-tile maximum overflows the fp32 sum: the result is
+    non-finite (loud), never a finite wrong number; within the limit the sweep is exact."""
+    rng = np.random.default_rng(3)
+    N, C, K, T = 8, 32, 1024, 0.07
+    unit = lambda n: O.l2_normalize(rng.standard_normal((n, C)).astype(np.float32))
+    q, k, mem = unit(N) * 12.0, unit(N), unit(K)
+    mem[900] = q[2] / 12.0                                    # logit 12 / 0.07 = 171 nats, far from tile 0 of its slice
+    lse, prob, dq = O.one_sweep_head(q, k, mem, T, tile=128, slices=2)
+    assert not np.isfinite(lse[2])
+    ok = [i for i in range(N) if i != 2]
+    out = O.MemoryMoCoOracle(mem, T).logits(q, k)
+    assert np.abs(lse[ok] - O.logsumexp_rows(out)[ok]).max() < 1e-3
+    lse1, _, dq1 = O.one_sweep_head(q / 12.0, k, mem, T, tile=128, slices=2)     # normalised features: exact
+    out1 = O.MemoryMoCoOracle(mem, T).logits(q / 12.0, k)
+    assert np.abs(lse1 - O.logsumexp_rows(out1)).max() < 2e-5 * np.abs(out1).max()
+    ref_dq = O.nce_backward_dq(q / 12.0, k, mem, T)
+    assert np.abs(dq1 - ref_dq).max() / np.abs(ref_dq).max() < 1e-4
