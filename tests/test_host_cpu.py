@@ -251,3 +251,22 @@ def test_python_flag_constants_match_the_header():
     bits = [enum["MOCO_NCE_" + n] for n in ("FORCE_SIMT", "CTA_PAIR", "SINGLE_CTA", "SHARE2", "SHARE4", "DQ_V1", "STATS_TS",
                                               "EPI8", "KPS1", "TWO_PASS", "ONE_PASS")]
     assert all(b & (b - 1) == 0 for b in bits) and len(set(bits)) == len(bits)
+
+
+def test_example_trainer_accepts_every_launcher_spelling(monkeypatch):
+    """the reference's --local_rank only parser breaks under torch >= 2.0 launchers; the example
+    entry point takes --local_rank, --local-rank and $LOCAL_RANK."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("train_moco_example", os.path.join(root, "examples", "train_moco.py"))
+    mod = importlib.util.module_from_spec(spec)
+    monkeypatch.delenv("LOCAL_RANK", raising=False)
+    spec.loader.exec_module(mod)
+    assert mod.parse_args([]).local_rank == 0
+    assert mod.parse_args(["--local_rank", "3"]).local_rank == 3
+    assert mod.parse_args(["--local-rank=5"]).local_rank == 5
+    monkeypatch.setenv("LOCAL_RANK", "6")
+    assert mod.parse_args([]).local_rank == 6
+    assert mod.parse_args(["--local-rank", "2"]).local_rank == 2
+    a = mod.parse_args(["--nce-k", "65536", "--nce-t", "0.2", "--persist-index"])
+    assert (a.nce_k, a.nce_t, a.persist_index) == (65536, 0.2, True)
