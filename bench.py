@@ -3,18 +3,21 @@
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # CPU arm: the oracle port of the reference step on host cores
+    python bench.py --impl reference ...      # CPU arm: the UNMODIFIED reference train_moco (oracle/_ref) on host cores
 
 A step = one MoCo iteration (train.py:244-283): query encoder fwd, ShuffleBN permute, key encoder fwd,
 un-shuffle, q.Queue^T + InfoNCE + dq, enqueue, backward, SGD step, EMA update -- ResNet-50, feat_dim 128,
 batch 256/GPU, bf16 autocast, synthetic 224x224 images, random-init weights.
-Workloads: N=1 -> BASELINE configs[1] (K=16384); N>1 -> configs[2] (K=65536, ShuffleBN over NVLink P2P).
+Workloads: N=1 -> BASELINE configs[1] (K=16384); N>1 -> configs[2] (K=65536, ShuffleBN over NVLink P2P) plus,
+in the same JSON line, a multi-GPU parity block (run BEFORE the timed region; the run fails if it does), the
+ShuffleBN permute timed alone and BASELINE configs[3] (K=131072 sharded over the ranks).
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -22,6 +25,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+
+METRIC = "MoCo pretrain images/sec (device-timed, max over ranks)"      # BASELINE.json:metric, same string in both arms
 
 
 def parse():
@@ -39,7 +44,12 @@ def parse():
                     help="encoder activation layout (host PyTorch side)")
     ap.add_argument("--no-stress", action="store_true", help="skip the c5 roofline-stress microbench")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--cpu-sample-batch", type=int, default=16,
+                    help="images per step of the CPU arm (a bounded sample of the 256-image batch)")
+    ap.add_argument("--no-c1", action="store_true", help="reference arm: skip BASELINE configs[0] (R18, K=1024, N=32)")
+    ap.add_argument("--no-sharded", action="store_true", help="N>1: skip the configs[3] sharded-queue block")
+    ap.add_argument("--ddp-bucket-mb", type=int, default=25)
+    ap.add_argument("--ddp-bf16", action="store_true", help="N>1: all-reduce gradients as bf16 (DDP compress hook)")
     return ap.parse_args()
 
 
@@ -92,29 +102,71 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def cpu_arm(args, steps, warmup):
-    from oracle.cpu_step import time_cpu_arm
-    K = args.nce_k or 16384
-    r = time_cpu_arm(args.arch, args.feat_dim, K, args.nce_t, args.cpu_sample_batch, steps, warmup)
-    return r, K
+def default_k(world):
+    return 16384 if world == 1 else 65536
+
+
+def workload_name(args, K, world):
+    return (f"{args.arch} feat_dim={args.feat_dim} K={K} batch={args.batch}/GPU bf16 "
+            + ("(BASELINE configs[1])" if world == 1 else "(BASELINE configs[2], ShuffleBN P2P permute)"))
+
+
+def config_block(args, K, world):
+    """`config` of the JSON line -- identical in the native and the reference arm (same workload by construction)."""
+    return {"workload": workload_name(args, K, world), "global_batch": args.batch * world,
+            "parallelism": f"dp{world}", "temperature": args.nce_t,
+            "l2": "native arm: inputs (308 MB/step) exceed L2, no explicit flush"}
+
+
+def reference_job(arch, feat_dim, K, T, batch, steps, warmup, timeout=900):
+    """The unmodified reference train_moco (oracle/ref_runner.py on oracle/_ref) in its OWN process: the shims
+    (identity .cuda(), gloo group) must not leak into this one, and its thread pool starts clean."""
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT",
+              "GROUP_RANK", "LOCAL_WORLD_SIZE", "ROLE_RANK", "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)                       # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every core
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py"), "--arch", arch, "--feat-dim", str(feat_dim),
+           "--nce-k", str(K), "--nce-t", str(T), "--batch", str(batch), "--steps", str(steps), "--warmup", str(warmup)]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    if p.returncode != 0 or not lines:
+        raise RuntimeError(f"reference CPU arm failed (rc={p.returncode}): {p.stderr[-2000:]}")
+    return json.loads(lines[-1])
+
+
+def cpu_baseline_block(r, extra=None):
+    b = {"value": r["images_per_s"], "unit": "images/s", "cores": r["threads"], "kind": "reference",
+         "sample": f"{r['warmup']} warm-up + {r['steps']} timed steps x {r['batch']} images of the UNMODIFIED reference "
+                   f"train.train_moco (train.py:231-293, staged in oracle/_ref) -- {r['arch']}, feat_dim={r['feat_dim']}, "
+                   f"K={r['K']}, fp32, gloo world 1, {r['threads']} host threads",
+         "ms_per_step": r["ms_per_step"], "loss": r["loss"]}
+    if extra:
+        b.update(extra)
+    return b
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    r, K = cpu_arm(args, args.steps, args.warmup)
-    cores = r["threads"]
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    K = args.nce_k or default_k(world)
+    steps, warmup = max(3, args.steps), max(3, args.warmup)
+    r = reference_job(args.arch, args.feat_dim, K, args.nce_t, args.cpu_sample_batch, steps, warmup)
+    extra = {}
+    if not args.no_c1:
+        # BASELINE configs[0] / SURVEY 8(d): the reference's own CPU-runnable case, full size (no sampling)
+        c1 = reference_job("resnet18", 128, 1024, args.nce_t, 32, 10, 3)
+        extra["c1"] = {"value": c1["images_per_s"], "unit": "images/s", "ms_per_step": c1["ms_per_step"],
+                       "cores": c1["threads"], "workload": "BASELINE configs[0]: ResNet-18 feat_dim=128 K=1024 batch=32 "
+                       "world 1, fp32, reference train_moco, 3 warm-up + 10 timed steps"}
     line = {
-        "impl": "reference", "metric": "MoCo pretrain images/sec", "value": r["images_per_s"], "unit": "images/s",
-        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "impl": "reference", "metric": METRIC, "value": r["images_per_s"], "unit": "images/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.arch} feat_dim={args.feat_dim} K={K} batch=256/GPU (BASELINE configs[1]); "
-                               f"CPU arm runs a bounded sample of {r['batch']} images/step"},
-        "cpu_baseline": {"value": r["images_per_s"], "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{r['steps']} steps x {r['batch']} images, oracle/cpu_step.py (numpy hot path + "
-                                   f"torch-CPU fp32 encoders), {cores} threads"},
+        "config": config_block(args, K, world),
+        "cpu_baseline": cpu_baseline_block(r, extra),
         "e2e": {"value": r["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -183,6 +235,113 @@ def stress_roofline(peaks, dev):
     }
 
 
+def shufflebn_block(x2, epoch, rank, world, dev, nhwc):
+    """ShuffleBN forward permute (util.py:69-79 replacement) timed ALONE on this step's key batch: the whole call
+    (publish into the peer-mapped staging buffer + signal barrier + P2P pull) and the pull kernel by itself.
+    CUDA events on the launching stream, max over ranks.  Collective."""
+    import torch
+    import torch.distributed as dist
+    from moco_b200 import _lib
+    from moco_b200.util import DistributedShufle, ShuffleContext
+    lib = _lib.load()
+    n = x2.shape[0]
+    iters = 10
+
+    def timed_us(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) * 1e3
+
+    fwd_us = timed_us(lambda: DistributedShufle.forward_shuffle(x2, epoch, cast_dtype=torch.bfloat16, channels_last=nhwc))
+    # the pull alone, on pre-staged data (bf16 rows = what crosses NVLink in the step)
+    ctx = ShuffleContext.get()
+    row_bytes = x2[0].numel() * 2
+    buf = ctx._staging("bench_fwd", n * row_bytes)
+    buf.tensor((n * row_bytes // 2,), torch.bfloat16).normal_()
+    ctx.barrier()
+    fwd_inds, _ = DistributedShufle.get_shuffle_ids(n * world, epoch, dev)
+    src = DistributedShufle.get_local_id(fwd_inds).contiguous()
+    out = torch.empty(n * row_bytes // 2, dtype=torch.bfloat16, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    gather_us = timed_us(lambda: lib.moco_shuffle_gather(buf.table, world, n, src.data_ptr(), n, row_bytes,
+                                                         out.data_ptr(), ctx.gather_flags, stream))
+    ctx.barrier()
+    remote = int(((src // n) != rank).sum().item())
+    rr = torch.tensor([float(remote)], device=dev)
+    dist.all_reduce(rr, op=dist.ReduceOp.MIN)
+    return {"fwd_us": fwd_us, "gather_us": gather_us, "remote_rows": remote, "rows": n, "row_bytes": row_bytes,
+            "gather_GBps": n * row_bytes / (gather_us * 1e-6) / 1e9,
+            "nvlink_GBps": remote * row_bytes / (gather_us * 1e-6) / 1e9,
+            "nvlink_frac_of_900": remote * row_bytes / (gather_us * 1e-6) / 1e9 / 900.0,
+            "note": "fwd_us = publish (crop+cast+layout into the peer-mapped staging buffer) + signal barrier + pull; "
+                    "gather_us = the pull kernel alone; nvlink_GBps counts only rows that live on another GPU "
+                    "(this rank's count; slowest rank's time)"}
+
+
+def sharded_block(args, model, model_ema, opt, x1, x2, epoch, rank, world, dev, nhwc, peaks, timed):
+    """BASELINE configs[3]: K = 131072 ring sharded over the ranks (ShardedMemoryMoCo), same step loop.
+    Reports images/s of the whole step, the head alone (all exchanges + kernels) and the exchange steps."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from moco_b200.NCE import ShardedMemoryMoCo
+    from moco_b200.train_step import MoCoStep
+    N, C, T, Ksh = args.batch, args.feat_dim, args.nce_t, 131072
+    smod = ShardedMemoryMoCo(C, Ksh, T).to(dev)
+    step = MoCoStep(model, model_ema, smod, opt, channels_last=nhwc)
+    steps = max(3, min(args.steps, 10))
+    for _ in range(3):
+        step(x1, x2, epoch)
+
+    def loop(k):
+        for _ in range(k):
+            step(x1, x2, epoch)
+    ms = timed(loop, steps)
+    # head alone: forward_loss (q exchange, shard sweep, statistics exchange, merge, gradient exchange) + backward
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    q = F.normalize(torch.randn(N, C, device=dev, generator=g), dim=1).requires_grad_(True)
+    k = F.normalize(torch.randn(N, C, device=dev, generator=g), dim=1)
+    k_all = torch.empty(N * world, C, device=dev)
+    dist.all_gather_into_tensor(k_all, k)
+    iters = 20
+
+    def head(kk):
+        for _ in range(kk):
+            q.grad = None
+            loss, _ = smod.forward_loss(q, k, k_all)
+            loss.backward()
+    head(3)
+    smod.profile = []
+    head(iters)
+    prof, smod.profile = smod.profile, None
+    torch.cuda.synchronize()
+    parts = {}
+    for name, e0, e1 in prof:
+        parts[name] = parts.get(name, 0.0) + e0.elapsed_time(e1) * 1e3 / iters
+    ms_head = timed(head, iters)
+    flops = 4.0 * (N * world) * C * (Ksh // world)              # per rank: all W*N queries x its shard, fwd + bwd
+    sweep = parts.get("shard_sweep_us")
+    return {"workload": f"BASELINE configs[3]: K={Ksh} sharded /{world} ({Ksh // world} rows per rank), "
+                        f"{N * world} queries per rank, same {args.arch} step",
+            "value": N * world * steps / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms / steps, "steps": steps,
+            "head_us": ms_head * 1e3 / iters, "parts_us": parts,
+            "shard_kernel": {"us": sweep, "algorithmic_flops": flops,
+                             "TFLOPs": (flops / (sweep * 1e-6) / 1e12) if sweep else None,
+                             "frac": (flops / (sweep * 1e-6) / 1e12 / peaks["tf_sustained"]) if sweep else None},
+            "note": "parts_us: CUDA events around each stage of the head on the launching stream (exchanges = "
+                    "publish + signal barrier + peer pull over NVLink; no NCCL on the data path)"}
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -211,7 +370,22 @@ def run_native(args):
     torch.backends.cudnn.allow_tf32 = True
 
     N, C, T = args.batch, args.feat_dim, args.nce_t
-    K = args.nce_k or (16384 if world == 1 else 65536)
+    K = args.nce_k or default_k(world)
+
+    # ---- multi-GPU parity, where the driver can see it (N > 1): ShuffleBN both directions + NHWC publish +
+    #      dist_collect bit-exact against the oracle of util.py:47-111, three sharded-queue steps against the
+    #      replicated oracle of Contrast.py:20-34.  Runs BEFORE the timed region; a failure fails the run.
+    parity = None
+    if world > 1:
+        from tools.multi_gpu_check import correctness
+        parity = correctness(rank, world, dev)
+        if not parity["ok_all_ranks"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "multi-GPU parity check failed", "parity": parity}))
+            dist.barrier()
+            dist.destroy_process_group()
+            sys.exit(1)
+
     torch.manual_seed(0)
     ctor = getattr(encoders, args.arch)
     mf = torch.channels_last if args.memory_format == "channels_last" else torch.contiguous_format
@@ -220,8 +394,18 @@ def run_native(args):
     model_ema.load_state_dict(model.state_dict())
     contrast = MemoryMoCo(C, K, T).to(dev)
     opt = torch.optim.SGD(model.parameters(), lr=0.03 * N * world / 256, momentum=0.9, weight_decay=1e-4)
+    ddp_cfg = None
     if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False)
+        # library DDP as in train.py:198 (out of scope, host PyTorch); only its knobs are set: gradients live in the
+        # bucket views (no grad->bucket copies), static graph (no per-step bucket rebuild checks)
+        ddp_cfg = {"bucket_cap_mb": args.ddp_bucket_mb, "gradient_as_bucket_view": True, "static_graph": True,
+                   "grad_comm_dtype": "bf16 (compress hook)" if args.ddp_bf16 else "f32"}
+        model = torch.nn.parallel.DistributedDataParallel(
+            model, device_ids=[local_rank], broadcast_buffers=False, bucket_cap_mb=args.ddp_bucket_mb,
+            gradient_as_bucket_view=True, static_graph=True)
+        if args.ddp_bf16:
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+            model.register_comm_hook(None, default_hooks.bf16_compress_hook)
     nhwc = args.memory_format == "channels_last"
     step = MoCoStep(model, model_ema, contrast, opt, channels_last=nhwc)
 
@@ -309,6 +493,12 @@ def run_native(args):
     h2d = N * 6 * 224 * 224 * 4
     final_loss = sink[-1][0]
 
+    shufflebn = sharded = None
+    if world > 1:
+        shufflebn = shufflebn_block(x2, epoch, rank, world, dev, nhwc)
+        if not args.no_sharded:
+            sharded = sharded_block(args, model, model_ema, opt, x1, x2, epoch, rank, world, dev, nhwc, peaks, timed)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -336,13 +526,10 @@ def run_native(args):
                 "one pipeline fill dominate; roofline_stress (N=1 runs) is the tensor-bound shape of BASELINE configs[4]",
     }
     line = {
-        "metric": "MoCo pretrain images/sec (device-timed, max over ranks)", "value": value, "unit": "images/s",
+        "metric": METRIC, "value": value, "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.arch} feat_dim={C} K={K} batch={N}/GPU bf16 "
-                               + ("(BASELINE configs[1])" if world == 1 else "(BASELINE configs[2], ShuffleBN P2P permute)"),
-                   "global_batch": N * world, "parallelism": f"dp{world}", "temperature": T,
-                   "l2": "inputs (308 MB/step) exceed L2; no explicit flush"},
+        "config": config_block(args, K, world),
         "clocks": sampler.result(),
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
@@ -350,13 +537,21 @@ def run_native(args):
         "roofline": roofline,
         "final_loss": final_loss,
     }
+    if parity is not None:
+        line["parity"] = {"shufflebn": parity["shufflebn"], "sharded": parity["sharded_queue"],
+                          "max_err": parity["max_err"], "world": world,
+                          "what": "ShuffleBN fwd/bwd + NHWC publish + dist_collect bit-exact vs the oracle of util.py:47-111; "
+                                  "3 sharded-queue steps vs the replicated oracle of Contrast.py:20-34 (all ranks)"}
+        line["ddp"] = ddp_cfg
+    if shufflebn is not None:
+        line["shufflebn"] = shufflebn
+    if sharded is not None:
+        line["sharded"] = sharded
     if world == 1 and not args.no_stress:
         line["roofline_stress"] = stress_roofline(peaks, dev)
     if world == 1 and not args.no_cpu_baseline:
-        r, Kc = cpu_arm(args, 2, 1)
-        line["cpu_baseline"] = {"value": r["images_per_s"], "unit": "images/s", "cores": r["threads"], "kind": "port",
-                                "sample": f"{r['steps']} steps x {r['batch']} images (same {args.arch}, K={Kc}), "
-                                          f"oracle/cpu_step.py on {r['threads']} host threads"}
+        r = reference_job(args.arch, C, K, T, args.cpu_sample_batch, 5, 3)
+        line["cpu_baseline"] = cpu_baseline_block(r)
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

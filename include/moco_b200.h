@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MOCO_B200_ABI_VERSION 1
+#define MOCO_B200_ABI_VERSION 2
 
 enum {
     MOCO_OK = 0,
@@ -39,19 +39,14 @@ enum {
 
 enum { MOCO_F32 = 0, MOCO_BF16 = 1 };
 
-/* moco_nce_fwd `flags` (0 = the tuned defaults; the rest select measured alternatives, see profiles/) */
+/* moco_nce_fwd `flags` (0 = the tuned defaults).  ABI 2 removed the round-1 variants that measured slower or
+ * time-neutral (TMA-multicast sharing, first-generation dq kernel, q-in-TMEM statistics kernel, 8-warp epilogue,
+ * one-chunk CTA-pair stages); their bit values (8, 16, 32, 64, 128, 256) stay reserved. */
 enum {
     MOCO_NCE_AUTO = 0,         /* tcgen05 kernels when the shape allows it (C % 64 == 0, C <= 256)   */
     MOCO_NCE_FORCE_SIMT = 1,   /* generic CUDA-core kernel (any shape)                               */
     MOCO_NCE_CTA_PAIR = 2,     /* statistics kernel on tcgen05.mma.cta_group::2 (M = 256 per pair)   */
     MOCO_NCE_SINGLE_CTA = 4,   /* require the tcgen05 path (error instead of the generic fallback)   */
-    MOCO_NCE_SHARE2 = 8,       /* share queue tiles across 2-CTA clusters by TMA multicast (halves   */
-                               /* L2 reads; measured time-neutral on B200, so off by default)         */
-    MOCO_NCE_SHARE4 = 16,      /* same with 4-CTA clusters                                            */
-    MOCO_NCE_DQ_V1 = 32,       /* first-generation dq kernel (P through shared memory)                */
-    MOCO_NCE_STATS_TS = 64,    /* statistics kernel with the q block in TMEM (192-row tiles)          */
-    MOCO_NCE_EPI8 = 128,       /* 8 epilogue warps instead of two ping-pong groups of 8               */
-    MOCO_NCE_KPS1 = 256,       /* CTA-pair statistics kernel: one 64-wide K chunk per smem stage (not 2) */
     MOCO_NCE_TWO_PASS = 512,   /* statistics pass, then dq pass normalised with the final lse (always exact) */
     MOCO_NCE_ONE_PASS = 1024   /* loss AND dq from one sweep over the queue (4NCK FLOP, NK exps instead of   */
                                /* 6NCK, 2NK): each (CTA, row) stabilises with the row maximum of the CTA's   */
@@ -169,6 +164,13 @@ int moco_nce_shard_dq(const void* q_all, int q_dtype, const void* shard_bf16, co
                       void* workspace, size_t workspace_bytes, int flags, void* stream);
 int moco_nce_shard_dq_finish(const float* o_own, const void* k_own, int k_dtype,
                              const float* prob_rows_own, int N, int C, float inv_T, float* dq, void* stream);
+/* The same last step with the reduce_scatter folded in: o_peers_host is a HOST array of `world` device pointers to
+ * every rank's [world*N, C] fp32 o_partial (peer-mapped staging buffers, moco_p2p_*); this rank's rows
+ * [rank*N, (rank+1)*N) of all of them are summed in rank order while dq is finished.  The caller orders the
+ * peers' writes before this call with moco_signal_barrier. */
+int moco_nce_shard_dq_finish_peers(const void* const* o_peers_host, int world, int rank, const void* k_own,
+                                   int k_dtype, const float* prob_rows_own, int N, int C, float inv_T,
+                                   float* dq, void* stream);
 int moco_queue_enqueue_shard(void* shard_bf16, float* shard_f32_or_null, const void* k_all, int k_dtype,
                              int n_all, int C, int64_t K, int64_t index,
                              int64_t shard_row0, int64_t shard_rows, void* stream);

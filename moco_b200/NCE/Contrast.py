@@ -76,6 +76,7 @@ class _FusedNCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, mod, flags):
         need_dq = q.requires_grad
+        ctx.set_materialize_grads(False)
         _, loss_prob, dq, _, _ = _nce_forward(mod, q.detach(), k.detach(), False, need_dq, flags)
         ctx.dq = dq
         ctx.q_dtype = q.dtype
@@ -86,7 +87,7 @@ class _FusedNCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, g_prob):
         dq = ctx.dq
-        if dq is None:
+        if dq is None or g_loss is None:
             return None, None, None, None
         return (dq * g_loss).to(ctx.q_dtype), None, None, None
 
@@ -98,14 +99,24 @@ class _FusedNCEWithLogits(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, mod, flags):
         need = q.requires_grad
+        # without this autograd hands backward() a zero-filled [N, K+1] gradient for `out` whenever only the
+        # loss was back-propagated (the reference call site, train.py:262-273): 67 MB of zeros per step at
+        # configs[2] plus a dense contraction over the whole queue, all to add 0
+        ctx.set_materialize_grads(False)
         logits, loss_prob, dq, qc, kc = _nce_forward(mod, q.detach(), k.detach(), True, need, flags)
         ctx.dq = dq
         ctx.q_dtype = q.dtype
         ctx.inv_T = 1.0 / mod.temperature
         ctx.K = mod.queue_size
         if need:
-            # the dense backward needs the PRE-enqueue queue (the reference clones it too, Contrast.py:25)
-            ctx.save_for_backward(kc, mod._queue_bf16().clone())
+            # The dense backward (a gradient arriving through `out` itself) needs the PRE-enqueue rows.  The
+            # reference clones the whole queue every step for that (Contrast.py:25); here only the <= all_size rows
+            # the coming enqueue overwrites are stashed -- by MemoryMoCo.forward, right before it enqueues -- and
+            # the backward patches them back into a copy only if that gradient really arrives.
+            ctx.save_for_backward(kc)
+            ctx.mod = mod
+            ctx.stash = None                       # (ring index, rows [n, C] bf16) set by MemoryMoCo.forward
+            mod._pending_dense_ctx = ctx
         loss, prob = loss_prob[0], loss_prob[1]
         ctx.mark_non_differentiable(prob)
         return logits, loss, prob
@@ -118,7 +129,16 @@ class _FusedNCEWithLogits(torch.autograd.Function):
         if g_loss is not None:
             grad = ctx.dq * g_loss
         if g_out is not None:
-            kc, queue_pre = ctx.saved_tensors
+            (kc,) = ctx.saved_tensors
+            queue_pre = ctx.mod._queue_bf16()
+            if ctx.stash is not None:              # rebuild the snapshot the forward saw
+                if ctx.mod._enqueue_count != ctx.stash[2] + 1:
+                    raise RuntimeError("MemoryMoCo: backward through the dense logits after a later step already "
+                                       "enqueued into the queue; call backward() before the next forward()")
+                queue_pre = queue_pre.clone()
+                idx0, rows = ctx.stash[0], ctx.stash[1]
+                ids = (torch.arange(rows.shape[0], device=rows.device) + idx0) % ctx.K
+                queue_pre[ids] = rows
             lib = _lib.load()
             g = g_out.contiguous().float()
             N, C = kc.shape
@@ -154,6 +174,8 @@ class MemoryMoCo(nn.Module):
         self.register_buffer('memory_bf16', torch.empty(0, dtype=torch.bfloat16), persistent=False)
         self._bf16_src = None      # (data_ptr, _version) of `memory` the bf16 copy was built from
         self._scratch = {}
+        self._enqueue_count = 0
+        self._pending_dense_ctx = None
         self.register_load_state_dict_post_hook(lambda m, keys: m._after_load())
 
     # -- checkpoint format (train.py:145,163): keys {'params', 'memory'}, fp32 [K, C] ------------------
@@ -178,9 +200,19 @@ class MemoryMoCo(nn.Module):
         self._scratch = {}
         return out
 
+    def _check_buffers(self):
+        """The C ABI takes raw pointers: `memory` must be exactly the fp32 row-major [K, C] buffer the kernels
+        index (module.half() / .double() / .to(dtype) convert registered buffers behind our back)."""
+        mem = self.memory
+        if mem.dtype != torch.float32 or not mem.is_contiguous() or mem.dim() != 2 or mem.shape[0] != self.queue_size:
+            raise RuntimeError(f"MemoryMoCo: `memory` must stay a contiguous float32 [queue_size, C] buffer "
+                               f"(got {mem.dtype}, shape {tuple(mem.shape)}); keep the module in fp32 -- the kernels "
+                               "maintain their own bf16 working copy")
+
     def _queue_bf16(self) -> torch.Tensor:
         mem = self.memory
         _lib.require_cuda(mem)
+        self._check_buffers()
         tag = (mem.data_ptr(), mem._version)
         if self._bf16_src != tag or self.memory_bf16.shape != mem.shape or self.memory_bf16.device != mem.device:
             if self.memory_bf16.shape != mem.shape or self.memory_bf16.device != mem.device:
@@ -197,6 +229,13 @@ class MemoryMoCo(nn.Module):
         lib = _lib.load()
         _lib.require_cuda(k_all)
         k_all = k_all.detach().contiguous()
+        if k_all.dim() != 2 or k_all.shape[1] != self.memory.shape[1]:
+            raise ValueError(f"MemoryMoCo.enqueue: k_all {tuple(k_all.shape)} does not match the queue "
+                             f"{tuple(self.memory.shape)}")
+        if k_all.device != self.memory.device:
+            raise RuntimeError(f"MemoryMoCo.enqueue: k_all on {k_all.device}, queue on {self.memory.device}")
+        if k_all.shape[0] > self.queue_size:
+            raise ValueError(f"MemoryMoCo.enqueue: {k_all.shape[0]} keys > queue_size {self.queue_size}")
         all_size, C = k_all.shape
         queue = self._queue_bf16()
         code = lib.moco_queue_enqueue(queue.data_ptr(), self.memory.data_ptr(), k_all.data_ptr(),
@@ -206,6 +245,7 @@ class MemoryMoCo(nn.Module):
         # the kernel wrote both copies; keep the cache tag in sync without bumping `memory._version`
         self._bf16_src = (self.memory.data_ptr(), self.memory._version)
         self.index = (self.index + all_size) % self.queue_size
+        self._enqueue_count += 1
 
     # -- public API ----------------------------------------------------------
     def forward_loss(self, q, k, k_all):
@@ -217,6 +257,13 @@ class MemoryMoCo(nn.Module):
 
     def forward(self, q, k, k_all):
         out, loss, prob = _FusedNCEWithLogits.apply(q, k.detach(), self, self.kernel_flags)
+        ctx, self._pending_dense_ctx = self._pending_dense_ctx, None
+        if ctx is not None:
+            # stash the rows this enqueue is about to overwrite (<= all_size x C bf16, e.g. 0.5 MB at configs[2])
+            # instead of cloning the whole queue (Contrast.py:25) for a backward that usually never comes
+            n = min(int(k_all.shape[0]), self.queue_size)
+            ids = (torch.arange(n, device=self.memory.device) + self.index) % self.queue_size
+            ctx.stash = (self.index, self._queue_bf16()[ids], self._enqueue_count)
         self.enqueue(k_all)
         # let NCESoftmaxLoss pick up the fused result instead of re-reading [N, K+1] logits
         out._moco_fused = (loss, prob, out._version)

@@ -12,8 +12,9 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_uint3
 
 from . import build as _build
 
+ABI_VERSION = 2                    # MOCO_B200_ABI_VERSION (include/moco_b200.h)
 MOCO_F32, MOCO_BF16 = 0, 1
-NCE_AUTO, NCE_FORCE_SIMT, NCE_CTA_PAIR, NCE_SINGLE_CTA, NCE_SHARE2, NCE_SHARE4, NCE_DQ_V1, NCE_STATS_TS, NCE_EPI8, NCE_KPS1 = 0, 1, 2, 4, 8, 16, 32, 64, 128, 256
+NCE_AUTO, NCE_FORCE_SIMT, NCE_CTA_PAIR, NCE_SINGLE_CTA = 0, 1, 2, 4
 NCE_TWO_PASS, NCE_ONE_PASS = 512, 1024
 ONE_PASS_MAX_INV_T = 25.0          # MOCO_ONE_PASS_MAX_INV_T (include/moco_b200.h)
 GATHER_AUTO, GATHER_LDG = 0, 1
@@ -38,6 +39,8 @@ SIGNATURES = {
     "moco_nce_shard_dq": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
                                   c_void_p, c_size_t, c_int, c_void_p]),
     "moco_nce_shard_dq_finish": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "moco_nce_shard_dq_finish_peers": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
+                                               c_float, c_void_p, c_void_p]),
     "moco_queue_enqueue_shard": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64,
                                          c_int64, c_int64, c_void_p]),
     "moco_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -78,7 +81,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.moco_abi_version() != 1:
+    if lib.moco_abi_version() != ABI_VERSION:
         raise RuntimeError("moco_b200: ABI version mismatch between _lib.py and libmoco_b200.so")
     _lib = _Counting(lib)
     return _lib
@@ -92,7 +95,7 @@ class _Counting:
     """Thin proxy over the CDLL that counts this library's kernel launches."""
 
     _PER_CALL = {"moco_nce_shard_stats": 3, "moco_nce_shard_merge": 1, "moco_nce_shard_dq": 2,
-                 "moco_nce_shard_dq_finish": 1, "moco_queue_enqueue_shard": 1, "moco_queue_enqueue": 1, "moco_f32_to_bf16": 1, "moco_shuffle_gather": 1,
+                 "moco_nce_shard_dq_finish": 1, "moco_nce_shard_dq_finish_peers": 1, "moco_queue_enqueue_shard": 1, "moco_queue_enqueue": 1, "moco_f32_to_bf16": 1, "moco_shuffle_gather": 1,
                  "moco_ema_update": 1, "moco_crop_to_nhwc_bf16": 1,
                  "moco_signal_barrier": 1, "moco_nce_bwd_dense": 1}
 
@@ -136,7 +139,7 @@ class _Counting:
             rc = fn(*a)
             if rc == 0:
                 simt = bool(a[16] & NCE_FORCE_SIMT) or a[5] % 64 != 0 or a[5] > 256
-                one_pass = (a[13] and not a[8] and not (a[16] & (NCE_TWO_PASS | NCE_DQ_V1))
+                one_pass = (a[13] and not a[8] and not (a[16] & NCE_TWO_PASS)
                             and ((a[16] & NCE_ONE_PASS) or a[7] <= ONE_PASS_MAX_INV_T))
                 # tcgen05 path: prep + one-pass kernel + combine + dq_reduce, or prep + stats + combine
                 # [+ dq + dq_reduce]; generic path: prep + row kernel

@@ -116,18 +116,14 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
         p.q_bf16 = qb; p.queue = queue; p.N = N; p.C = C; p.K = K; p.inv_T = inv_T; p.logits = logits;
         p.cta_group = (flags & MOCO_NCE_CTA_PAIR) ? 2 : 1;
         p.num_sms = d.sms;
-        const int max_share = (flags & MOCO_NCE_SHARE4) ? 4 : ((flags & MOCO_NCE_SHARE2) ? 2 : 1);
-        p.max_share = max_share;
-        p.epi_warps = (flags & MOCO_NCE_EPI8) ? 8 : 16;
-        p.kps1 = (flags & MOCO_NCE_KPS1) ? 1 : 0;
         p.slices = 0; p.n_pad = 0;
         // one sweep over the queue for loss + gradient when that is numerically safe (include/moco_b200.h)
-        const bool one_pass = dq && !logits && !(flags & (MOCO_NCE_TWO_PASS | MOCO_NCE_DQ_V1)) &&
+        const bool one_pass = dq && !logits && !(flags & MOCO_NCE_TWO_PASS) &&
                               ((flags & MOCO_NCE_ONE_PASS) || inv_T <= MOCO_ONE_PASS_MAX_INV_T);
         if (one_pass) {
             int slices = 0, n_pad = 0;
             prof_mark(MOCO_PROF_DQ, 0, stream);
-            e = launch_nce_dq2_tc(qb, queue, N, C, K, inv_T, nullptr, d.sms, max_share, &slices, &n_pad, ws, stream);
+            e = launch_nce_dq2_tc(qb, queue, N, C, K, inv_T, nullptr, d.sms, &slices, &n_pad, ws, stream);
             prof_mark(MOCO_PROF_DQ, 1, stream);
             if (e == cudaSuccess) {
                 e = launch_combine(N, C, slices, n_pad, inv_T, nullptr, K, lse, loss_rows, prob_rows, loss_prob, ws, stream);
@@ -141,7 +137,7 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
             // shape outside the one-pass kernel's envelope: two-pass below
         }
         prof_mark(MOCO_PROF_STATS, 0, stream);
-        e = (flags & MOCO_NCE_STATS_TS) ? launch_nce_stats3(p, p.epi_warps, ws, stream) : launch_nce_tc(p, ws, stream);
+        e = launch_nce_tc(p, ws, stream);
         prof_mark(MOCO_PROF_STATS, 1, stream);
         if (e == cudaSuccess) {
             e = launch_combine(N, C, p.slices, p.n_pad, inv_T, logits, K, lse, loss_rows, prob_rows, loss_prob, ws, stream);
@@ -149,10 +145,7 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
             if (dq) {
                 int slices = 0, n_pad = 0;
                 prof_mark(MOCO_PROF_DQ, 0, stream);
-                if (flags & MOCO_NCE_DQ_V1)
-                    e = launch_nce_dq_tc(qb, queue, N, C, K, inv_T, lse, d.sms, max_share, &slices, &n_pad, ws, stream);
-                else
-                    e = launch_nce_dq2_tc(qb, queue, N, C, K, inv_T, lse, d.sms, max_share, &slices, &n_pad, ws, stream);
+                e = launch_nce_dq2_tc(qb, queue, N, C, K, inv_T, lse, d.sms, &slices, &n_pad, ws, stream);
                 prof_mark(MOCO_PROF_DQ, 1, stream);
                 if (e != cudaSuccess) return cuda_fail("tcgen05 dq kernel", e);
                 e = launch_dq_reduce(N, C, slices, n_pad, inv_T, k, qk_dtype, prob_rows, dq, ws.part_o, stream);
@@ -257,17 +250,14 @@ int moco_nce_shard_stats(const void* q_all, const void* k_all, int qk_dtype, con
     p.N = N; p.C = C; p.K = Ks; p.inv_T = inv_T; p.logits = nullptr;
     p.cta_group = (flags & MOCO_NCE_CTA_PAIR) ? 2 : 1;
     p.num_sms = d.sms;
-    p.max_share = (flags & MOCO_NCE_SHARE4) ? 4 : ((flags & MOCO_NCE_SHARE2) ? 2 : 1);
-    p.epi_warps = (flags & MOCO_NCE_EPI8) ? 8 : 16;
-    p.kps1 = (flags & MOCO_NCE_KPS1) ? 1 : 0;
     p.slices = 0; p.n_pad = 0;
     if (flags & MOCO_NCE_ONE_PASS) {
         // one sweep over the shard: (stabiliser, sum) partials for the cross-rank merge AND the unnormalised
         // P~.Queue partials, which stay in the workspace until moco_nce_shard_dq(..., MOCO_NCE_ONE_PASS) rescales them
-        e = launch_nce_dq2_tc(p.q_bf16, p.queue, N, C, Ks, inv_T, nullptr, d.sms, p.max_share, &p.slices, &p.n_pad, ws, stream);
+        e = launch_nce_dq2_tc(p.q_bf16, p.queue, N, C, Ks, inv_T, nullptr, d.sms, &p.slices, &p.n_pad, ws, stream);
         if (e != cudaSuccess) return cuda_fail("tcgen05 one-pass kernel", e);
     } else {
-        e = (flags & MOCO_NCE_STATS_TS) ? launch_nce_stats3(p, p.epi_warps, ws, stream) : launch_nce_tc(p, ws, stream);
+        e = launch_nce_tc(p, ws, stream);
         if (e != cudaSuccess) return cuda_fail("tcgen05 stats kernel", e);
     }
     e = launch_combine_partial(N, p.slices, p.n_pad, static_cast<float2*>(ms_out), ws, stream);
@@ -301,23 +291,19 @@ int moco_nce_shard_dq(const void* q_all, int q_dtype, const void* shard_bf16, co
     if (!shard_bf16 || !lse_all || !o_partial) { set_error("moco_nce_shard_dq: null pointer"); return MOCO_ERR_INVALID; }
     // q_bf16 in the workspace was produced by moco_nce_shard_stats on the same workspace (fp32 inputs)
     const __nv_bfloat16* qb = q_dtype == MOCO_BF16 ? static_cast<const __nv_bfloat16*>(q_all) : ws.q_bf16;
-    const int max_share = (flags & MOCO_NCE_SHARE4) ? 4 : ((flags & MOCO_NCE_SHARE2) ? 2 : 1);
     int slices = 0, n_pad = 0;
     cudaError_t e;
     if (flags & MOCO_NCE_ONE_PASS) {
         // the sweep already happened in moco_nce_shard_stats(..., MOCO_NCE_ONE_PASS) on this workspace: only the
         // slice count is needed, then O = sum_s 2^(m_s - lse) O~_s
-        e = launch_nce_dq2_tc(qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, nullptr, d.sms, max_share,
+        e = launch_nce_dq2_tc(qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, nullptr, d.sms,
                               &slices, &n_pad, ws, stream, /*plan_only=*/true);
         if (e != cudaSuccess) return cuda_fail("one-pass plan", e);
         e = launch_dq_reduce(N, C, slices, n_pad, inv_T, nullptr, 0, nullptr, o_partial, ws.part_o, stream, ws.part_ms, lse_all);
         if (e != cudaSuccess) return cuda_fail("dq reduce kernel", e);
         return MOCO_OK;
     }
-    if (flags & MOCO_NCE_DQ_V1)
-        e = launch_nce_dq_tc(qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, lse_all, d.sms, max_share, &slices, &n_pad, ws, stream);
-    else
-        e = launch_nce_dq2_tc(qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, lse_all, d.sms, max_share, &slices, &n_pad, ws, stream);
+    e = launch_nce_dq2_tc(qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, lse_all, d.sms, &slices, &n_pad, ws, stream);
     if (e != cudaSuccess) return cuda_fail("tcgen05 dq kernel", e);
     e = launch_dq_reduce(N, C, slices, n_pad, inv_T, nullptr, 0, nullptr, o_partial, ws.part_o, stream);
     if (e != cudaSuccess) return cuda_fail("dq reduce kernel", e);
@@ -334,6 +320,25 @@ int moco_nce_shard_dq_finish(const float* o_own, const void* k_own, int k_dtype,
     cudaError_t e = launch_dq_reduce(N, C, 1, N, inv_T, k_own, k_dtype, prob_rows_own, dq, o_own,
                                      static_cast<cudaStream_t>(stream_));
     if (e != cudaSuccess) return cuda_fail("dq finish kernel", e);
+    return MOCO_OK;
+}
+
+int moco_nce_shard_dq_finish_peers(const void* const* o_peers_host, int world, int rank, const void* k_own, int k_dtype,
+                                   const float* prob_rows_own, int N, int C, float inv_T, float* dq, void* stream_) {
+    g_err[0] = 0;
+    if (!o_peers_host || !k_own || !prob_rows_own || !dq || N <= 0 || C <= 0 || (C & 3) || world < 1 || world > 16 ||
+        rank < 0 || rank >= world) {
+        set_error("moco_nce_shard_dq_finish_peers: bad argument");
+        return MOCO_ERR_INVALID;
+    }
+    for (int r = 0; r < world; ++r)
+        if (!o_peers_host[r] || (reinterpret_cast<uintptr_t>(o_peers_host[r]) & 15)) {
+            set_error("moco_nce_shard_dq_finish_peers: peer %d pointer null or misaligned", r);
+            return MOCO_ERR_INVALID;
+        }
+    cudaError_t e = launch_dq_finish_peers(o_peers_host, world, rank, N, C, inv_T, k_own, k_dtype, prob_rows_own, dq,
+                                           static_cast<cudaStream_t>(stream_));
+    if (e != cudaSuccess) return cuda_fail("dq finish (peers) kernel", e);
     return MOCO_OK;
 }
 

@@ -77,6 +77,8 @@ cudaError_t launch_combine(int N, int C, int slices, int n_pad, float inv_T, flo
 cudaError_t launch_dq_reduce(int N, int C, int slices, int n_pad, float inv_T, const void* k, int k_dtype,
                              const float* prob_rows, float* dq, const float* part_o, cudaStream_t stream,
                              const float2* part_ms = nullptr, const float* lse = nullptr);
+cudaError_t launch_dq_finish_peers(const void* const* peers_host, int world, int rank, int N, int C, float inv_T,
+                                   const void* k, int k_dtype, const float* prob_rows, float* dq, cudaStream_t stream);
 cudaError_t launch_combine_partial(int N, int slices, int n_pad, float2* ms_out, const NceWorkspace& ws,
                                    cudaStream_t stream);
 cudaError_t launch_combine_merge(int N, int world, float inv_T, const float2* ms_all, float* lse, float* loss_rows,
@@ -105,21 +107,14 @@ struct NceTcParams {
     float* logits;                 // optional dense [N, K+1]
     int cta_group;                 // 1 or 2
     int num_sms;
-    int max_share;                 // upper bound on the TMA-multicast cluster size (1, 2 or 4)
-    int epi_warps;                 // 8 or 16 epilogue warps
-    int kps1;                      // 1: CTA-pair kernel with one (instead of two) K chunks per smem stage
     // outputs of the launch decision
     int slices;
     int n_pad;
 };
 cudaError_t launch_nce_tc(NceTcParams& p, const NceWorkspace& ws, cudaStream_t stream);
-cudaError_t launch_nce_stats3(NceTcParams& p, int epi_warps, const NceWorkspace& ws, cudaStream_t stream);
 cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* queue, int N, int C, int K,
-                              float inv_T, const float* lse, int num_sms, int max_share, int* slices_out,
+                              float inv_T, const float* lse, int num_sms, int* slices_out,
                               int* n_pad_out, const NceWorkspace& ws, cudaStream_t stream, bool plan_only = false);
-cudaError_t launch_nce_dq_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* queue, int N, int C, int K,
-                             float inv_T, const float* lse, int num_sms, int max_share, int* slices_out, int* n_pad_out,
-                             const NceWorkspace& ws, cudaStream_t stream);
 
 void set_error(const char* fmt, ...);
 

@@ -9,8 +9,7 @@
 // TMEM map (512 columns): q [0, C/2) | O [128, 128 + C) | S/P buffers 0 and 1 in the top 2*BN columns.
 // BN (queue rows per tile) is 128 when C <= 128 and 64 when C = 192/256 (O then needs up to 256 columns);
 // tcgen05.mma with N = 64 only reaches ~48 % of peak (tools/umma_bench.cu), so the wider tile matters.
-// Queue tiles are BN rows x C (C/64 slabs of BN x 128 B, 128B swizzle), 4-8 stage TMA ring; optional
-// TMA-multicast sharing across a cluster of CS CTAs that own different q row blocks.
+// Queue tiles are BN rows x C (C/64 slabs of BN x 128 B, 128B swizzle), 4-8 stage TMA ring.
 // Two MMA-issuing threads (S and P.V), see the kernel body; S(i+2) overwriting the buffer PV(i) reads P from is
 // ordered by the s_free mbarrier that PV(i)'s tcgen05.commit arrives on.
 //
@@ -56,7 +55,7 @@ struct Dq2Args {
     float2* part_ms;          // [slices, n_pad] (stabiliser, sum) in the log2 domain (one-pass mode)
 };
 
-template <int CS, int BN, bool FUSED, bool ISS2>
+template <int BN, bool FUSED, bool ISS2>
 __global__ void __launch_bounds__(kDq2Threads, 1)
 nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_constant__ CUtensorMap tm_unused,
                const Dq2Args a) {
@@ -87,13 +86,8 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
     float* exch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr bool kClustered = CS > 1;
-    constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
-    const uint32_t crank = kClustered ? cluster_ctarank() : 0u;
-    const int cluster_id = blockIdx.x / CS;
-    const int mgroups = a.mblks / CS;
-    const int mblk = (cluster_id % mgroups) * CS + (int)crank;
-    const int slice = cluster_id / mgroups;
+    const int mblk = blockIdx.x % a.mblks;
+    const int slice = blockIdx.x / a.mblks;
     const int t0 = (int)(((long long)slice * a.num_tiles) / a.slices);
     const int t1 = (int)(((long long)(slice + 1) * a.num_tiles) / a.slices);
     const int ntiles = t1 - t0;
@@ -103,7 +97,7 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
     // ---- set-up that touches no global memory (overlaps the predecessor kernel under PDL) ----
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_queue);     // kernel parameter space, not global data
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], CS); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); mbar_init(&s_free[b], 1); }
         mbar_init(o_full, 1);
         mbar_init(q_ready, 4);
@@ -128,7 +122,7 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
             if (v < qpre_n) qpre[v] = __ldg(src + v);
     }
     tc_fence_before();
-    if (kClustered) cluster_sync_all(); else __syncthreads();
+    __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) MOCO_TR(3, 0, 1);                       // barriers initialised, TMEM allocated
@@ -143,13 +137,7 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
                 mbar_arrive_expect_tx(&kv_full[st], (uint32_t)tile_bytes);
                 for (int kc = 0; kc < kchunks; ++kc) {
                     uint8_t* dst = v_s + (size_t)st * tile_bytes + kc * kSlab64;
-                    if (CS > 1) {
-                        constexpr int kPart = kDq2BN / CS;
-                        tma_load_2d_mc(&tm_queue, &kv_full[st], dst + (size_t)crank * kPart * 128, kc * 64,
-                                       (t0 + i) * kDq2BN + (int)crank * kPart, kMask);
-                    } else {
-                        tma_load_2d(&tm_queue, &kv_full[st], dst, kc * 64, (t0 + i) * kDq2BN);
-                    }
+                    tma_load_2d(&tm_queue, &kv_full[st], dst, kc * 64, (t0 + i) * kDq2BN);
                 }
             }
         }
@@ -208,7 +196,7 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
                                o_vdesc + (uint64_t)(kk * 128), idesc_o, (uint32_t)((i | kk) != 0));
                 }
                 MOCO_TR(0, i, 2);
-                if (CS > 1) umma_commit_mc(&kv_empty[o_st], kMask); else umma_commit<1>(&kv_empty[o_st]);
+                umma_commit<1>(&kv_empty[o_st]);
                 MOCO_TR(0, i, 3);
                 o_vdesc += tile_units;
                 if (++o_st == NS) { o_st = 0; o_vdesc = vm_desc0; }
@@ -279,7 +267,7 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
                                o_vdesc + (uint64_t)(kk * 128), idesc_o, (uint32_t)((i | kk) != 0));
                 }
                 MOCO_TR(0, i, 2);
-                if (CS > 1) umma_commit_mc(&kv_empty[o_st], kMask); else umma_commit<1>(&kv_empty[o_st]);
+                umma_commit<1>(&kv_empty[o_st]);
                 if (i + 2 < ntiles) umma_commit<1>(&s_free[b]);
                 MOCO_TR(0, i, 3);
                 o_vdesc += tile_units;
@@ -453,7 +441,7 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
     if (warp == 4 && lane == 0) MOCO_TR(3, 0, 4);                 // O written
     __syncwarp();
     tc_fence_before();
-    if (kClustered) cluster_sync_all(); else __syncthreads();
+    __syncthreads();
     if (threadIdx.x == 0) MOCO_TR(3, 0, 5);                       // all roles done
     if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
@@ -461,13 +449,12 @@ nce_dq2_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_consta
 // lse == nullptr selects the one-pass mode: the kernel also writes ws.part_ms (see the header comment).
 // plan_only: launch nothing, just report the slice count / padded rows this shape gets (sharded one-pass finish).
 cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* queue, int N, int C, int K,
-                              float inv_T, const float* lse, int num_sms, int max_share, int* slices_out,
+                              float inv_T, const float* lse, int num_sms, int* slices_out,
                               int* n_pad_out, const NceWorkspace& ws, cudaStream_t stream, bool plan_only) {
     const bool fused = (lse == nullptr);
     if (C % 64 != 0 || C < 64 || C > 256) return cudaErrorNotSupported;
     const int kchunks = C / 64;
     const int mblks = (N + 127) / 128;
-    const int CS = pick_share(mblks, max_share);
     if (mblks > num_sms) return cudaErrorNotSupported;
     const int BN = (C <= 128) ? 128 : 64;
     const int num_tiles = (K + BN - 1) / BN;
@@ -475,7 +462,7 @@ cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* 
     *n_pad_out = n_pad;
 
     CUtensorMap tm_queue;
-    if (!make_tmap(&tm_queue, queue, K, C, BN / CS)) return cudaErrorUnknown;
+    if (!make_tmap(&tm_queue, queue, K, C, BN)) return cudaErrorUnknown;
 
     const int tile_bytes = kchunks * BN * 128;
     int stages = (kSmemBudget - 2048) / tile_bytes;      // 2 KB: barriers + the one-pass exchange array
@@ -492,27 +479,19 @@ cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* 
     a.part_o = ws.part_o;
     a.part_ms = ws.part_ms;
     auto fill = [](Dq2Args& x, int slices) { x.slices = slices; };
-    static KernelCache kc[12];
-    const int mgroups = mblks / CS;
-#define MOCO_DQ2_LAUNCH(CS_, BN_, IDX)                                                                             \
+#define MOCO_DQ2_LAUNCH(BN_, IDX)                                                                                  \
     do {                                                                                                           \
         constexpr bool kIss2 = (BN_ == 64);                                                                        \
         if (fused)                                                                                                 \
-            return plan_and_launch(nce_dq2_kernel<CS_, BN_, true, kIss2>, kc[6 + IDX], kDq2Threads, smem, CS_,     \
-                                   mgroups, mblks, num_tiles, n_pad, slices_out, stream, tm_queue, tm_queue, a,    \
+            return plan_and_launch(nce_dq2_kernel<BN_, true, kIss2>, kernel_cache(2 + IDX), kDq2Threads, smem, 1,  \
+                                   mblks, mblks, num_tiles, n_pad, slices_out, stream, tm_queue, tm_queue, a,      \
                                    fill, true, plan_only);                                                         \
-        return plan_and_launch(nce_dq2_kernel<CS_, BN_, false, kIss2>, kc[IDX], kDq2Threads, smem, CS_, mgroups,   \
+        return plan_and_launch(nce_dq2_kernel<BN_, false, kIss2>, kernel_cache(IDX), kDq2Threads, smem, 1, mblks,  \
                                mblks, num_tiles, n_pad, slices_out, stream, tm_queue, tm_queue, a, fill, true,     \
                                plan_only);                                                                         \
     } while (0)
-    if (BN == 128) {
-        if (CS == 4) MOCO_DQ2_LAUNCH(4, 128, 0);
-        if (CS == 2) MOCO_DQ2_LAUNCH(2, 128, 1);
-        MOCO_DQ2_LAUNCH(1, 128, 2);
-    }
-    if (CS == 4) MOCO_DQ2_LAUNCH(4, 64, 3);
-    if (CS == 2) MOCO_DQ2_LAUNCH(2, 64, 4);
-    MOCO_DQ2_LAUNCH(1, 64, 5);
+    if (BN == 128) MOCO_DQ2_LAUNCH(128, 0);
+    MOCO_DQ2_LAUNCH(64, 1);
 #undef MOCO_DQ2_LAUNCH
 }
 

@@ -237,6 +237,49 @@ cudaError_t launch_dq_reduce(int N, int C, int slices, int n_pad, float inv_T, c
                       prob_rows, dq, part_ms, lse);
 }
 
+// Sharded queue, last step: dq_i = inv_T / N * ( sum_r O_r[row0 + i] + (prob_i - 1) k_i ), the W partial-gradient
+// blocks O_r read straight from the peers' staging buffers over NVLink (replaces an NCCL reduce_scatter); ranks are
+// summed in index order, so every run gives the same bits.  One block per row, C/4 float4 lanes.
+struct PeerOTable { const float* base[16]; };
+
+__global__ void dq_finish_peers_kernel(PeerOTable peers, int world, int row0, int N, int C, float inv_T,
+                                       const void* __restrict__ k, int k_dtype, const float* __restrict__ prob_rows,
+                                       float* __restrict__ dq) {
+    const int i = blockIdx.x;
+    const int lanes = C >> 2;
+    for (int lane = threadIdx.x; lane < lanes; lane += blockDim.x) {
+        float4 v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r)                      // all peer loads in flight before the first add
+            if (r < world) v[r] = __ldcv(reinterpret_cast<const float4*>(peers.base[r] + (size_t)(row0 + i) * C) + lane);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            if (r < world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+        const size_t base = (size_t)i * C + lane * 4;
+        const float gscale = inv_T / (float)N;
+        const float pm1 = prob_rows[i] - 1.f;
+        float4 o;
+        o.x = gscale * (acc.x + pm1 * load_as_float(k, k_dtype, base + 0));
+        o.y = gscale * (acc.y + pm1 * load_as_float(k, k_dtype, base + 1));
+        o.z = gscale * (acc.z + pm1 * load_as_float(k, k_dtype, base + 2));
+        o.w = gscale * (acc.w + pm1 * load_as_float(k, k_dtype, base + 3));
+        *reinterpret_cast<float4*>(dq + base) = o;
+    }
+}
+
+cudaError_t launch_dq_finish_peers(const void* const* peers_host, int world, int rank, int N, int C, float inv_T,
+                                   const void* k, int k_dtype, const float* prob_rows, float* dq, cudaStream_t stream) {
+    if ((C & 3) != 0 || world < 1 || world > 16) return cudaErrorNotSupported;
+    PeerOTable t;
+    for (int r = 0; r < 16; ++r) t.base[r] = r < world ? static_cast<const float*>(peers_host[r]) : nullptr;
+    int threads = C >> 2;
+    if (threads > 256) threads = 256;
+    if (threads < 32) threads = 32;
+    dq_finish_peers_kernel<<<N, threads, 0, stream>>>(t, world, rank * N, N, C, inv_T, k, k_dtype, prob_rows, dq);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------
 // Generic CUDA-core path: one block per q row, any (N, C <= 1024, K).
 // ---------------------------------------------------------------------------

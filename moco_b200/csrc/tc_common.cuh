@@ -4,6 +4,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -54,6 +56,17 @@ struct KernelCache {
     int smem_set = -1;
     int q_smem = -1, q_cluster = -1, q_result = 0;
 };
+
+// cudaFuncSetAttribute and the occupancy answer are per DEVICE: one cache entry per (device ordinal, kernel slot of
+// this translation unit), all guarded by one mutex (launches from several host threads / several GPUs in one process).
+constexpr int kMaxDevices = 64, kCacheSlots = 8;
+static std::mutex g_kernel_cache_mutex;
+static KernelCache& kernel_cache(int slot) {
+    static KernelCache table[kMaxDevices][kCacheSlots];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return table[dev][slot];
+}
 
 template <typename Kern>
 static cudaError_t prepare_kernel(Kern kern, KernelCache& kc, int threads, int smem, int cluster, int* max_clusters) {
@@ -122,7 +135,11 @@ static cudaError_t plan_and_launch(Kern kern, KernelCache& kc, int threads, int 
                                    const CUtensorMap& a, const CUtensorMap& b, Args& args, Fill fill, bool pdl = false,
                                    bool plan_only = false) {
     int max_clusters = 0;
-    cudaError_t e = prepare_kernel(kern, kc, threads, smem, cluster, &max_clusters);
+    cudaError_t e;
+    {
+        std::lock_guard<std::mutex> lock(g_kernel_cache_mutex);
+        e = prepare_kernel(kern, kc, threads, smem, cluster, &max_clusters);
+    }
     if (e != cudaSuccess) return e;
     int slices = max_clusters / mgroups;            // one persistent wave
     if (slices > num_tiles) slices = num_tiles;
@@ -135,19 +152,11 @@ static cudaError_t plan_and_launch(Kern kern, KernelCache& kc, int threads, int 
     return launch_cluster(kern, ctas_per_slice * slices, threads, smem, cluster, stream, a, b, args, pdl);
 }
 
-// largest multicast cluster size in {4, 2, 1} that divides the number of q row blocks
 // bring-up switch for pipeline experiments (never set in production): see StatsArgs::debug
 inline int debug_mode() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("MOCO_DEBUG_MODE"); v = e ? atoi(e) : 0; }
     return v;
 }
-
-inline int pick_share(int mblks, int max_share) {
-    if (max_share >= 4 && mblks % 4 == 0) return 4;
-    if (max_share >= 2 && mblks % 2 == 0) return 2;
-    return 1;
-}
-
 
 }  // namespace moco

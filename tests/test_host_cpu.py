@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert ctypes.cast(getattr(raw, n), ctypes.c_void_p).value
         assert callable(getattr(lib, n))
-    assert lib.moco_abi_version() == 1
+    assert lib.moco_abi_version() == _lib.ABI_VERSION == 2
     assert lib.moco_nce_workspace_bytes(256, 128, 16384) > 0
 
 
@@ -169,8 +169,25 @@ def _shard_worker(rank, world, port, ret):
     from moco_b200.NCE import ShardedMemoryMoCo
     torch.manual_seed(3)
     m = ShardedMemoryMoCo(128, 64, 0.07)
-    ret[rank] = dict(row0=m.shard_row0, rows=m.shard_rows, memory=m.memory.numpy().copy(),
-                     keys=sorted(m.state_dict().keys()))
+    mem0 = m.memory.numpy().copy()
+    # checkpoint contract: state_dict() returns the FULL [K, C] queue by pulling the peers' shards, which needs the
+    # shards peer-mapped (first step / share_memory_across_ranks, CUDA only) -- before that it must refuse loudly
+    # rather than silently save 1/W of the queue
+    try:
+        m.state_dict()
+        refused = False
+    except RuntimeError as exc:
+        refused = "peer-mapped" in str(exc)
+    # load: a full [K, C] queue (reference / MemoryMoCo checkpoint) keeps this rank's block; a bare shard loads as is
+    full = torch.arange(64 * 128, dtype=torch.float32).view(64, 128)
+    m.load_state_dict({"params": torch.tensor([-1]), "memory": full})
+    took_block = bool(torch.equal(m.memory, full[m.shard_row0:m.shard_row0 + m.shard_rows]))
+    m.load_state_dict({"params": torch.tensor([-1]), "memory": full[:32] + 1})
+    took_shard = bool(torch.equal(m.memory, full[:32] + 1))
+    p = ShardedMemoryMoCo(128, 64, 0.07, persist_index=True)
+    p.load_state_dict({"params": torch.tensor([40]), "memory": full})
+    ret[rank] = dict(row0=m.shard_row0, rows=m.shard_rows, memory=mem0, refused=refused, took_block=took_block,
+                     took_shard=took_shard, index=p.index, keys=sorted(k for k, _ in m.named_buffers()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -186,7 +203,9 @@ def test_sharded_queue_block_layout_world2_gloo():
     full = MemoryMoCo(128, 64, 0.07).memory.numpy()
     assert [ret[r]["row0"] for r in range(2)] == [0, 32] and all(ret[r]["rows"] == 32 for r in range(2))
     np.testing.assert_array_equal(np.concatenate([ret[0]["memory"], ret[1]["memory"]]), full)
-    assert ret[0]["keys"] == ["memory", "params"]
+    assert ret[0]["keys"] == ["memory", "memory_bf16", "params"]
+    for r in range(2):
+        assert ret[r]["refused"] and ret[r]["took_block"] and ret[r]["took_shard"] and ret[r]["index"] == 40
     with pytest.raises(ValueError, match="divisible"):
         # world size 1 here: any K is divisible, so emulate the check directly
         from moco_b200.NCE import ShardedContrast
@@ -241,15 +260,13 @@ def test_python_flag_constants_match_the_header():
     from moco_b200 import _lib
     text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "moco_b200.h")).read()
     enum = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(MOCO_[A-Z0-9_]+)\s*=\s*(-?\d+)", text)}
-    for name in ("AUTO", "FORCE_SIMT", "CTA_PAIR", "SINGLE_CTA", "SHARE2", "SHARE4", "DQ_V1", "STATS_TS", "EPI8", "KPS1",
-                 "TWO_PASS", "ONE_PASS"):
+    for name in ("AUTO", "FORCE_SIMT", "CTA_PAIR", "SINGLE_CTA", "TWO_PASS", "ONE_PASS"):
         assert getattr(_lib, "NCE_" + name) == enum["MOCO_NCE_" + name], name
     assert _lib.MOCO_F32 == enum["MOCO_F32"] and _lib.MOCO_BF16 == enum["MOCO_BF16"]
     limit = float(re.search(r"#define\s+MOCO_ONE_PASS_MAX_INV_T\s+([0-9.]+)f", text).group(1))
     assert _lib.ONE_PASS_MAX_INV_T == limit
     # every flag is a distinct bit
-    bits = [enum["MOCO_NCE_" + n] for n in ("FORCE_SIMT", "CTA_PAIR", "SINGLE_CTA", "SHARE2", "SHARE4", "DQ_V1", "STATS_TS",
-                                              "EPI8", "KPS1", "TWO_PASS", "ONE_PASS")]
+    bits = [enum["MOCO_NCE_" + n] for n in ("FORCE_SIMT", "CTA_PAIR", "SINGLE_CTA", "TWO_PASS", "ONE_PASS")]
     assert all(b & (b - 1) == 0 for b in bits) and len(set(bits)) == len(bits)
 
 

@@ -14,10 +14,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-FLAGS = {"auto": 0, "simt": 1, "tc2": 2, "tc1": 4, "tc1_nomc": 4, "tc1_s2": 12, "tc1_s4": 20,
-         "dq2": 4, "dq2_nomc": 4, "dq2_s2": 12, "dq2_s4": 20, "dq1": 36, "v1": 4, "e16": 4, "e8": 132, "ts": 68,
-         "ts8": 196, "v1e16": 4, "tc2e16": 2, "tc2e8": 130, "tc2kps1": 258,
-         "op": 4 | 1024, "op_s2": 12 | 1024, "op_s4": 20 | 1024, "tp": 4 | 512}
+FLAGS = {"auto": 0, "simt": 1, "tc2": 2, "tc1": 4, "op": 4 | 1024, "tp": 4 | 512}
 # name: (N, C, K, T, flagname, want_logits, timing_iters)
 NCE_CASES = {
     "simt_small": (32, 128, 1024, 0.07, "simt", True, 0),
@@ -32,43 +29,16 @@ NCE_CASES = {
     "tc1_c5": (512, 256, 262144, 0.07, "tc1", False, 10),
     "tc2_c5": (512, 256, 262144, 0.07, "tc2", False, 10),
     "tc1_c3_dense": (256, 128, 65536, 0.07, "tc1", True, 5),
-    "nomc_c5": (512, 256, 262144, 0.07, "tc1_nomc", False, 10),
-    "s4_c5": (512, 256, 262144, 0.07, "tc1_s4", False, 10),
-    "nomc_c3": (256, 128, 65536, 0.07, "tc1_nomc", False, 20),
     "tc1_c4": (2048, 128, 16384, 0.07, "tc1", False, 20),
-    "s4_c4": (2048, 128, 16384, 0.07, "tc1_s4", False, 20),
-    "s4_ragged": (500, 192, 3000, 0.1, "tc1_s4", True, 0),
     "tc1_ragged2": (300, 64, 5000, 0.1, "tc1", True, 0),
-    "tc2kps1_c5": (512, 256, 262144, 0.07, "tc2kps1", False, 10),
-    "e8_c5": (512, 256, 262144, 0.07, "e8", False, 10),
-    "ts_c5": (512, 256, 262144, 0.07, "ts", False, 10),
-    "dq1_c5": (512, 256, 262144, 0.07, "dq1", False, 10),
-    "dq1_c3": (256, 128, 65536, 0.07, "dq1", False, 20),
-    "ts_ragged": (200, 192, 1000, 0.1, "ts", True, 0),
-    "e8_ragged": (200, 192, 1000, 0.1, "e8", True, 0),
-    "dq1_ragged": (200, 192, 1000, 0.1, "dq1", True, 0),
-    "v1_c5": (512, 256, 262144, 0.07, "v1", False, 10),
-    "v1e16_c5": (512, 256, 262144, 0.07, "v1e16", False, 10),
-    "tc2e16_c5": (512, 256, 262144, 0.07, "tc2e16", False, 10),
-    "v1e16_c3": (256, 128, 65536, 0.07, "v1e16", False, 20),
-    "v1_c3": (256, 128, 65536, 0.07, "v1", False, 20),
-    "v1_c2": (256, 128, 16384, 0.07, "v1", False, 20),
-    "v1e16_ragged": (200, 192, 1000, 0.1, "v1e16", True, 0),
-    "tc2e16_ragged": (200, 192, 1000, 0.1, "tc2e16", True, 0),
-    "e16_c5": (512, 256, 262144, 0.07, "e16", False, 10),
-    "e16_c3": (256, 128, 65536, 0.07, "e16", False, 20),
-    "e16_ragged": (200, 192, 1000, 0.1, "e16", True, 0),
-    "v1_ragged": (200, 192, 1000, 0.1, "v1", True, 0),
     # one sweep for loss + dq ("op") vs statistics pass + dq pass ("tp")
     "op_small": (32, 128, 1024, 0.07, "op", False, 0),
     "op_ragged": (200, 192, 1000, 0.1, "op", False, 0),
     "op_ragged2": (300, 64, 5000, 0.1, "op", False, 0),
-    "op_s4_ragged": (500, 256, 3000, 0.1, "op_s4", False, 0),
     "op_c2": (256, 128, 16384, 0.07, "op", False, 20),
     "op_c3": (256, 128, 65536, 0.07, "op", False, 20),
     "op_c4": (2048, 128, 16384, 0.07, "op", False, 20),
     "op_c5": (512, 256, 262144, 0.07, "op", False, 10),
-    "op_s2_c5": (512, 256, 262144, 0.07, "op_s2", False, 10),
     "tp_small": (32, 128, 1024, 0.07, "tp", False, 0),
     "tp_ragged": (200, 192, 1000, 0.1, "tp", False, 0),
     "tp_c64": (100, 64, 777, 0.07, "tp", False, 0),
@@ -77,15 +47,6 @@ NCE_CASES = {
     "tp_c2": (256, 128, 16384, 0.07, "tp", False, 20),
     "tp_c3": (256, 128, 65536, 0.07, "tp", False, 20),
     "tp_c5": (512, 256, 262144, 0.07, "tp", False, 10),
-    "dq2_small": (32, 128, 1024, 0.07, "dq2", False, 0),
-    "dq2_c64": (100, 64, 777, 0.07, "dq2", False, 0),
-    "dq2_ragged": (200, 192, 1000, 0.1, "dq2", False, 0),
-    "dq2_s4_ragged": (500, 256, 3000, 0.1, "dq2_s4", False, 0),
-    "dq2_c2": (256, 128, 16384, 0.07, "dq2", False, 20),
-    "dq2_c3": (256, 128, 65536, 0.07, "dq2", False, 20),
-    "dq2_c4": (2048, 128, 16384, 0.07, "dq2", False, 20),
-    "dq2_c5": (512, 256, 262144, 0.07, "dq2", False, 10),
-    "dq2_nomc_c5": (512, 256, 262144, 0.07, "dq2_nomc", False, 10),
 }
 
 

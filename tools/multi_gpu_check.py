@@ -20,11 +20,10 @@ from moco_b200.util import DistributedShufle, ShuffleContext, dist_collect  # no
 from oracle import moco_oracle as O  # noqa: E402
 
 
-def main():
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+def correctness(rank, world, dev):
+    """ShuffleBN (both directions, double-buffer reuse, bf16/NHWC publish), dist_collect and three sharded-queue
+    steps against the numpy oracle of the reference (util.py:47-111, Contrast.py:20-34).  Also called by bench.py
+    before its timed region at N > 1 (the `parity` block of the JSON line).  Collective: every rank calls it."""
     res = {"world": world, "ok": True}
 
     def batch(r, n, shape, seed):
@@ -86,9 +85,33 @@ def main():
         e_dq = float(np.abs(qt.grad.cpu().numpy() - ref_dq).max() / np.abs(ref_dq).max())
         ok_s = ok_s and e_l < 2e-4 and e_p < 1e-3 and e_dq < 5e-3 and smod.index == orc.index
         res[f"sharded_step{step}"] = [e_l, e_p, e_dq]
+    torch.cuda.synchronize()
+    dist.barrier()                      # every rank's last enqueue has completed (a training loop has DDP's all-reduce here)
     ok_s = ok_s and np.array_equal(smod.full_memory().cpu().numpy(), orc.memory)
+    if rank == 0:                       # the reference checkpoints on rank 0 only (train.py:226-228): no collective allowed
+        sd = smod.state_dict()
+        ok_s = ok_s and sorted(sd) == ["memory", "params"] and tuple(sd["memory"].shape) == (K, C) \
+            and np.array_equal(sd["memory"].cpu().numpy(), orc.memory)
+    dist.barrier()
     res["sharded_queue"] = bool(ok_s)
     res["ok"] = res["ok"] and bool(ok_s)
+    res["max_err"] = {"loss_abs": max(res[f"sharded_step{i}"][0] for i in range(3)),
+                      "prob_rel": max(res[f"sharded_step{i}"][1] for i in range(3)),
+                      "dq_rel": max(res[f"sharded_step{i}"][2] for i in range(3)), "shufflebn": "bit-exact"}
+    res["shufflebn"] = all(v for k, v in res.items() if k.startswith(("iter", "nhwc", "dist_collect")))
+    flag = torch.tensor([1.0 if res["ok"] else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # parity must hold on EVERY rank
+    res["ok_all_ranks"] = bool(flag.item() > 0.5)
+    return res
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    res = correctness(rank, world, dev)
+    res["ok"] = res["ok"] and res["ok_all_ranks"]
 
     # ---- bandwidth: BASELINE batch (256 x 3 x 224 x 224), fp32 and bf16, bulk-async vs LDG kernels
     ctx = ShuffleContext.get()
