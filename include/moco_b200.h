@@ -49,13 +49,15 @@ enum {
     MOCO_NCE_SINGLE_CTA = 4,   /* require the tcgen05 path (error instead of the generic fallback)   */
     MOCO_NCE_TWO_PASS = 512,   /* statistics pass, then dq pass normalised with the final lse (always exact) */
     MOCO_NCE_ONE_PASS = 1024   /* loss AND dq from one sweep over the queue (4NCK FLOP, NK exps instead of   */
-                               /* 6NCK, 2NK): each (CTA, row) stabilises with the row maximum of the CTA's   */
-                               /* first tile; exact unless a later logit exceeds that maximum by > ~88 nats, */
-                               /* then that row's loss is inf/NaN (never silently wrong).  AUTO picks it     */
-                               /* when dq is requested, logits are not, and inv_T <= MOCO_ONE_PASS_MAX_INV_T */
-                               /* (L2-normalised q and queue rows of norm <= sqrt(3) -- the reference's      */
-                               /* U(-s, s) initial queue, Contrast.py:16-17 -- then span <= 2 sqrt(3) inv_T  */
-                               /* <= 88 nats); TWO_PASS otherwise.                                            */
+                               /* 6NCK, 2NK) plus ONE tail kernel: each (CTA, row) stabilises with the row   */
+                               /* maximum of the CTA's first tile.  A row whose partial sum leaves the safe  */
+                               /* range (a later logit > ~100 binades above that maximum: un-normalised      */
+                               /* inputs) is detected by the tail kernel and recomputed exactly on CUDA      */
+                               /* cores, so the result always equals the reference's.  AUTO picks it when dq */
+                               /* is requested, logits are not, and inv_T <= MOCO_ONE_PASS_MAX_INV_T (with   */
+                               /* L2-normalised q and queue rows of norm <= sqrt(3) -- the reference's       */
+                               /* U(-s, s) initial queue, Contrast.py:16-17 -- the fallback never triggers); */
+                               /* TWO_PASS otherwise.                                                         */
 };
 #define MOCO_ONE_PASS_MAX_INV_T 25.0f
 
@@ -98,6 +100,37 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype,
                  float* logits_or_null, float* lse, float* loss_rows, float* prob_rows,
                  float* loss_prob, float* dq_or_null,
                  void* workspace, size_t workspace_bytes, int flags, void* stream);
+
+/* ------------------------------------------------------------------------
+ * One MoCo head step in TWO launches: moco_nce_fwd (one-sweep mode, no dense
+ * logits) fused with moco_queue_enqueue, i.e. MemoryMoCo.forward
+ * (moco/NCE/Contrast.py:20-36) + NCESoftmaxLoss (NCECriterion.py:11-13) + `prob`
+ * (train.py:264) + the gradient of train.py:273:
+ *
+ *   kernel 1  the q.Queue^T sweep on tcgen05 (reads q as given, no cast kernel);
+ *   kernel 2  merge -> lse / loss / prob, weighted sum of the partial gradients -> dq,
+ *             then queue[(index + i) mod K] = k_all[i] for i in [0, n_all), and the
+ *             ring position advanced on the device when `index_dev` is given.
+ *
+ * normalize != 0: q, k and k_all arrive UN-normalised (the encoder's fc output,
+ * moco/models/resnet.py:125-126,177-178); the rows are L2-normalised inside the
+ * kernels exactly like the reference's Normalize layer (resnet.py:24-33,
+ * x / sqrt(sum x^2)) and dq is the gradient w.r.t. the RAW q (the backward of the
+ * normalisation is applied in kernel 2).  Supported for C in {64, 128}.
+ *
+ * index / index_dev: the ring position BEFORE the call, by value, or -- when
+ * index_dev != NULL -- read from that device int64 and advanced there
+ * ((index + n_all) mod K, Contrast.py:34) by kernel 2, so a CUDA graph capturing
+ * this call replays correctly step after step.  queue_f32 may be NULL.
+ * Shapes outside the one-sweep envelope fall back to the moco_nce_fwd kernels
+ * followed by the enqueue kernel (then normalize and index_dev must be 0/NULL:
+ * MOCO_ERR_UNSUPPORTED otherwise).
+ * ---------------------------------------------------------------------- */
+int moco_nce_step(const void* q, const void* k, int qk_dtype, int normalize,
+                  void* queue_bf16, float* queue_f32_or_null, int N, int C, int K, float inv_T,
+                  const void* k_all, int k_all_dtype, int n_all, int64_t index, int64_t* index_dev_or_null,
+                  float* lse, float* loss_rows, float* prob_rows, float* loss_prob, float* dq,
+                  void* workspace, size_t workspace_bytes, int flags, void* stream);
 
 /* Profiling hook (bench.py's roofline): while set, moco_nce_fwd records the CUDA
  * events `ev_start` / `ev_stop` (cudaEvent_t) on its stream immediately before /

@@ -39,12 +39,17 @@ class _Scratch:
         self.ws_ptr = self.ws.data_ptr() + off
 
 
-def _nce_forward(mod: "MemoryMoCo", q, k, want_logits: bool, want_dq: bool, flags: int):
+def _nce_forward(mod: "MemoryMoCo", q, k, want_logits: bool, want_dq: bool, flags: int, k_all=None,
+                 normalize: bool = False):
+    """One head evaluation.  With ``k_all`` the FIFO enqueue (Contrast.py:29-34) is part of the same C call
+    (``moco_nce_step``: two kernels for loss, prob, dq and the enqueue) and the module's ring position is advanced."""
     lib = _lib.load()
     _lib.require_cuda(q, k, mod.memory)
     if q.dim() != 2 or q.shape != k.shape or q.shape[1] != mod.memory.shape[1]:
         raise ValueError(f"MemoryMoCo: q {tuple(q.shape)} / k {tuple(k.shape)} do not match the queue "
                          f"{tuple(mod.memory.shape)}")
+    if q.device != mod.memory.device or k.device != mod.memory.device:
+        raise RuntimeError(f"MemoryMoCo: q on {q.device}, k on {k.device}, queue on {mod.memory.device}")
     if q.dtype != k.dtype:
         k = k.to(q.dtype)
     q = q.contiguous()
@@ -59,25 +64,41 @@ def _nce_forward(mod: "MemoryMoCo", q, k, want_logits: bool, want_dq: bool, flag
     logits = torch.empty(N, K + 1, dtype=torch.float32, device=q.device) if want_logits else None
     dq = torch.empty(N, C, dtype=torch.float32, device=q.device) if want_dq else None
     loss_prob = torch.empty(2, dtype=torch.float32, device=q.device)
-    code = lib.moco_nce_fwd(
-        q.data_ptr(), k.data_ptr(), _lib.dtype_code(q), queue.data_ptr(), N, C, K,
-        1.0 / mod.temperature,
-        logits.data_ptr() if logits is not None else None,
-        sc.lse.data_ptr(), sc.loss_rows.data_ptr(), sc.prob_rows.data_ptr(), loss_prob.data_ptr(),
-        dq.data_ptr() if dq is not None else None,
-        sc.ws_ptr, sc.ws_bytes, flags, _lib.cur_stream())
-    _lib.check(code, "moco_nce_fwd")
+    if k_all is None:
+        if normalize:
+            raise RuntimeError("MemoryMoCo: in-kernel normalisation is part of the fused step (k_all required)")
+        code = lib.moco_nce_fwd(
+            q.data_ptr(), k.data_ptr(), _lib.dtype_code(q), queue.data_ptr(), N, C, K,
+            1.0 / mod.temperature,
+            logits.data_ptr() if logits is not None else None,
+            sc.lse.data_ptr(), sc.loss_rows.data_ptr(), sc.prob_rows.data_ptr(), loss_prob.data_ptr(),
+            dq.data_ptr() if dq is not None else None,
+            sc.ws_ptr, sc.ws_bytes, flags, _lib.cur_stream())
+        _lib.check(code, "moco_nce_fwd")
+    else:
+        k_all = mod._check_keys(k_all)
+        idx_dev = mod._index_dev()
+        code = lib.moco_nce_step(
+            q.data_ptr(), k.data_ptr(), _lib.dtype_code(q), 1 if normalize else 0, queue.data_ptr(),
+            mod.memory.data_ptr(), N, C, K, 1.0 / mod.temperature, k_all.data_ptr(), _lib.dtype_code(k_all),
+            k_all.shape[0], mod.index, idx_dev.data_ptr() if idx_dev is not None else None,
+            sc.lse.data_ptr(), sc.loss_rows.data_ptr(), sc.prob_rows.data_ptr(), loss_prob.data_ptr(),
+            dq.data_ptr() if dq is not None else None, sc.ws_ptr, sc.ws_bytes, flags, _lib.cur_stream())
+        _lib.check(code, "moco_nce_step")
+        mod._after_enqueue(k_all.shape[0])
     return logits, loss_prob, dq, q, k
 
 
 class _FusedNCE(torch.autograd.Function):
-    """(loss, prob) = InfoNCE(q, k, queue); backward: grad_q = grad_loss * dq (dq from the forward)."""
+    """(loss, prob) = InfoNCE(q, k, queue), then the enqueue of k_all -- one C call, two kernels.
+    backward: grad_q = grad_loss * dq (dq comes out of the forward's kernels)."""
 
     @staticmethod
-    def forward(ctx, q, k, mod, flags):
+    def forward(ctx, q, k, k_all, mod, flags, normalize):
         need_dq = q.requires_grad
         ctx.set_materialize_grads(False)
-        _, loss_prob, dq, _, _ = _nce_forward(mod, q.detach(), k.detach(), False, need_dq, flags)
+        _, loss_prob, dq, _, _ = _nce_forward(mod, q.detach(), k.detach(), False, need_dq, flags, k_all=k_all.detach(),
+                                              normalize=normalize)
         ctx.dq = dq
         ctx.q_dtype = q.dtype
         loss, prob = loss_prob[0], loss_prob[1]
@@ -88,8 +109,8 @@ class _FusedNCE(torch.autograd.Function):
     def backward(ctx, g_loss, g_prob):
         dq = ctx.dq
         if dq is None or g_loss is None:
-            return None, None, None, None
-        return (dq * g_loss).to(ctx.q_dtype), None, None, None
+            return None, None, None, None, None, None
+        return (dq * g_loss).to(ctx.q_dtype), None, None, None, None, None
 
 
 class _FusedNCEWithLogits(torch.autograd.Function):
@@ -153,9 +174,13 @@ class _FusedNCEWithLogits(torch.autograd.Function):
 class MemoryMoCo(nn.Module):
     """Fixed-size queue with momentum encoder (drop-in for moco.NCE.MemoryMoCo)."""
 
-    def __init__(self, feature_dim, queue_size, temperature=0.07, persist_index=False):
+    def __init__(self, feature_dim, queue_size, temperature=0.07, persist_index=False, device_index=False):
         super().__init__()
         self.queue_size = queue_size
+        # device_index=True keeps a device copy of the ring position that the kernels advance (CUDA-graph replay)
+        self.device_index = bool(device_index)
+        self._index_t = None
+        self._index_shadow = 0
         self.temperature = temperature
         self.index = 0
         self.kernel_flags = _lib.NCE_AUTO
@@ -181,11 +206,14 @@ class MemoryMoCo(nn.Module):
     # -- checkpoint format (train.py:145,163): keys {'params', 'memory'}, fp32 [K, C] ------------------
     def _save_to_state_dict(self, destination, prefix, keep_vars):
         if self.persist_index:
+            if self.device_index:
+                self.sync_index()                         # graph replays advance only the device copy
             self.params.fill_(int(self.index))
         super()._save_to_state_dict(destination, prefix, keep_vars)
 
     def _after_load(self):
         self._invalidate()
+        self._index_t = None
         if self.persist_index:
             saved = int(self.params.item())
             self.index = saved % self.queue_size if saved >= 0 else 0
@@ -198,6 +226,7 @@ class MemoryMoCo(nn.Module):
         out = super()._apply(fn, *a, **kw)
         self._invalidate()
         self._scratch = {}
+        self._index_t = None
         return out
 
     def _check_buffers(self):
@@ -224,36 +253,76 @@ class MemoryMoCo(nn.Module):
         return self.memory_bf16
 
     # -- enqueue (Contrast.py:29-34) ----------------------------------------
-    @torch.no_grad()
-    def enqueue(self, k_all):
-        lib = _lib.load()
+    def _check_keys(self, k_all):
         _lib.require_cuda(k_all)
         k_all = k_all.detach().contiguous()
         if k_all.dim() != 2 or k_all.shape[1] != self.memory.shape[1]:
-            raise ValueError(f"MemoryMoCo.enqueue: k_all {tuple(k_all.shape)} does not match the queue "
+            raise ValueError(f"MemoryMoCo: k_all {tuple(k_all.shape)} does not match the queue "
                              f"{tuple(self.memory.shape)}")
         if k_all.device != self.memory.device:
-            raise RuntimeError(f"MemoryMoCo.enqueue: k_all on {k_all.device}, queue on {self.memory.device}")
-        if k_all.shape[0] > self.queue_size:
-            raise ValueError(f"MemoryMoCo.enqueue: {k_all.shape[0]} keys > queue_size {self.queue_size}")
+            raise RuntimeError(f"MemoryMoCo: k_all on {k_all.device}, queue on {self.memory.device}")
+        return k_all
+
+    def _index_dev(self):
+        """Device copy of the ring position (``device_index=True``): the kernels read it and advance it themselves,
+        so a CUDA graph that captured the step replays correctly (the Python ``index`` stays a host mirror)."""
+        if not self.device_index:
+            return None
+        if self._index_t is None or self._index_t.device != self.memory.device:
+            self._index_t = torch.tensor([int(self.index)], dtype=torch.int64, device=self.memory.device)
+        elif self._index_shadow != self.index:            # somebody assigned `index` on the host
+            self._index_t.fill_(int(self.index))
+        self._index_shadow = self.index
+        return self._index_t
+
+    def sync_index(self):
+        """Refresh the host mirror ``index`` from the device copy (after CUDA-graph replays)."""
+        if self._index_t is not None:
+            self.index = int(self._index_t.item())
+        return self.index
+
+    def _after_enqueue(self, all_size):
+        # the kernel wrote both copies; keep the cache tag in sync without bumping `memory._version`
+        self._bf16_src = (self.memory.data_ptr(), self.memory._version)
+        self.index = (self.index + all_size) % self.queue_size
+        self._index_shadow = self.index                   # the fused step advanced the device copy too
+        self._enqueue_count += 1
+
+    @torch.no_grad()
+    def enqueue(self, k_all):
+        lib = _lib.load()
+        k_all = self._check_keys(k_all)
         all_size, C = k_all.shape
+        if self._index_t is not None and self.device_index:
+            self._index_t.fill_(int(self.index))          # stand-alone enqueue: host index is the source of truth
         queue = self._queue_bf16()
         code = lib.moco_queue_enqueue(queue.data_ptr(), self.memory.data_ptr(), k_all.data_ptr(),
                                       _lib.dtype_code(k_all), all_size, C, self.queue_size, self.index,
                                       _lib.cur_stream())
         _lib.check(code, "moco_queue_enqueue")
-        # the kernel wrote both copies; keep the cache tag in sync without bumping `memory._version`
-        self._bf16_src = (self.memory.data_ptr(), self.memory._version)
-        self.index = (self.index + all_size) % self.queue_size
-        self._enqueue_count += 1
+        self._after_enqueue(all_size)
+        if self._index_t is not None and self.device_index:
+            self._index_t.fill_(int(self.index))
 
     # -- public API ----------------------------------------------------------
-    def forward_loss(self, q, k, k_all):
+    def _can_fuse_normalize(self, q) -> bool:
+        flags = self.kernel_flags
+        return (q.requires_grad and q.shape[1] in (64, 128) and not (flags & (_lib.NCE_TWO_PASS | _lib.NCE_FORCE_SIMT))
+                and ((flags & _lib.NCE_ONE_PASS) or 1.0 / self.temperature <= _lib.ONE_PASS_MAX_INV_T))
+
+    def forward_loss(self, q, k, k_all, normalize=False):
         """Fused path: returns (loss, prob) == (NCESoftmaxLoss()(out), softmax(out,1)[:,0].mean())
-        of the reference's train.py:262-264, then enqueues k_all."""
-        loss, prob = _FusedNCE.apply(q, k.detach(), self, self.kernel_flags)
-        self.enqueue(k_all)
-        return loss, prob
+        of the reference's train.py:262-264 and enqueues k_all -- two kernels in all (``moco_nce_step``).
+
+        normalize=True: q, k, k_all are the encoders' RAW fc outputs; the rows are L2-normalised inside the kernels
+        exactly like the reference's ``Normalize`` layer (moco/models/resnet.py:24-33) and the gradient that flows
+        back is w.r.t. the raw q.  Shapes the kernels do not fuse are normalised here in torch."""
+        if normalize and not self._can_fuse_normalize(q):
+            q = q / q.pow(2).sum(1, keepdim=True).pow(0.5)
+            k = k / k.pow(2).sum(1, keepdim=True).pow(0.5)
+            k_all = k_all / k_all.pow(2).sum(1, keepdim=True).pow(0.5)
+            normalize = False
+        return _FusedNCE.apply(q, k.detach(), k_all.detach(), self, self.kernel_flags, bool(normalize))
 
     def forward(self, q, k, k_all):
         out, loss, prob = _FusedNCEWithLogits.apply(q, k.detach(), self, self.kernel_flags)

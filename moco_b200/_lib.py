@@ -28,6 +28,9 @@ SIGNATURES = {
     "moco_nce_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_size_t, c_int, c_void_p]),
+    "moco_nce_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                              c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_size_t, c_int, c_void_p]),
     "moco_prof_set_events": (c_int, [c_int, c_void_p, c_void_p]),
     "moco_nce_bwd_dense": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
                                    c_void_p, c_void_p]),
@@ -105,6 +108,8 @@ class _Counting:
             fn = getattr(lib, name)
             if name == "moco_nce_fwd":
                 setattr(self, name, self._wrap_nce(fn))
+            elif name == "moco_nce_step":
+                setattr(self, name, self._wrap_step(fn))
             elif name == "moco_nce_shard_dq":      # one-pass finish: dq_reduce only; two-pass: dq kernel + dq_reduce
                 setattr(self, name, self._wrap_flags(fn, 11))
             elif name in self._PER_CALL:
@@ -133,17 +138,36 @@ class _Counting:
         return call
 
     @staticmethod
-    def _wrap_nce(fn):
+    def _head_launches(C, inv_T, flags, dq, logits, f32):
+        """Kernels one head evaluation launches (mirrors the dispatch in csrc/capi.cu)."""
+        simt = bool(flags & NCE_FORCE_SIMT) or C % 64 != 0 or C > 256
+        if simt:
+            return 2                                             # prep + row kernel
+        one_pass = (dq and not logits and not (flags & NCE_TWO_PASS)
+                    and ((flags & NCE_ONE_PASS) or inv_T <= ONE_PASS_MAX_INV_T))
+        if one_pass:                                             # sweep + tail (+ prep for the bf16 copy at C > 128)
+            return 2 + (1 if (C > 128 and f32) else 0)
+        return 5 if dq else 3                                    # prep + stats + combine [+ dq + dq_reduce]
+
+    @classmethod
+    def _wrap_nce(cls, fn):
         def call(*a):
             global launches
             rc = fn(*a)
             if rc == 0:
-                simt = bool(a[16] & NCE_FORCE_SIMT) or a[5] % 64 != 0 or a[5] > 256
-                one_pass = (a[13] and not a[8] and not (a[16] & NCE_TWO_PASS)
-                            and ((a[16] & NCE_ONE_PASS) or a[7] <= ONE_PASS_MAX_INV_T))
-                # tcgen05 path: prep + one-pass kernel + combine + dq_reduce, or prep + stats + combine
-                # [+ dq + dq_reduce]; generic path: prep + row kernel
-                launches += 2 if simt else (4 if one_pass else (5 if a[13] else 3))
+                launches += cls._head_launches(a[5], a[7], a[16], a[13], a[8], a[2] == MOCO_F32)
+            return rc
+        return call
+
+    @classmethod
+    def _wrap_step(cls, fn):
+        def call(*a):
+            global launches
+            rc = fn(*a)
+            if rc == 0:
+                n = cls._head_launches(a[7], a[9], a[22], True, False, a[2] == MOCO_F32)
+                fused = n <= 3 and a[7] % 8 == 0 and 256 % (a[7] // 8) == 0      # the tail kernel also enqueues
+                launches += n + (0 if (fused or a[12] == 0) else 1)
             return rc
         return call
 

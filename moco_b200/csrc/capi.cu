@@ -74,68 +74,115 @@ size_t moco_nce_workspace_bytes(int N, int C, int K) {
     return carve_workspace(nullptr, N, C).bytes;
 }
 
-int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_bf16, int N, int C, int K,
-                 float inv_T, float* logits, float* lse, float* loss_rows, float* prob_rows, float* loss_prob,
-                 float* dq, void* workspace, size_t workspace_bytes, int flags, void* stream_) {
+}  // extern "C"
+
+// The q.Queue^T sweep (one-sweep mode when lse == nullptr): C in {64, 128} on nce_head128_sm100.cu, which reads q as
+// given (fp32/bf16, optional L2 normalisation); C in {192, 256} on nce_dq2_sm100.cu, which needs the bf16 copy `qb`.
+static cudaError_t launch_sweep(const void* q, int q_dtype, int normalize, const __nv_bfloat16* qb,
+                                const __nv_bfloat16* queue, int N, int C, int K, float inv_T, const float* lse, int sms,
+                                int* slices, int* n_pad, const NceWorkspace& ws, cudaStream_t stream,
+                                bool plan_only = false) {
+    if (C == 64 || C == 128)
+        return launch_nce_head128(q, q_dtype, normalize, queue, N, C, K, inv_T, lse, sms, slices, n_pad, ws, stream, plan_only);
+    if (normalize) return cudaErrorNotSupported;
+    return launch_nce_dq2_tc(qb, queue, N, C, K, inv_T, lse, sms, slices, n_pad, ws, stream, plan_only);
+}
+
+struct EnqueueSpec {            // n_all == 0: no enqueue
+    void* queue_bf16; float* queue_f32; const void* k_all; int k_dtype; int n_all;
+    long long index; long long* index_dev;
+};
+
+static int nce_head(const void* q, const void* k, int qk_dtype, int normalize, const void* queue_bf16, int N, int C,
+                    int K, float inv_T, float* logits, float* lse, float* loss_rows, float* prob_rows, float* loss_prob,
+                    float* dq, void* workspace, size_t workspace_bytes, int flags, const EnqueueSpec& enq,
+                    cudaStream_t stream, const char* who) {
     g_err[0] = 0;
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!q || !k || !queue_bf16 || !lse || !loss_rows || !prob_rows || !loss_prob || !workspace) {
-        set_error("moco_nce_fwd: null pointer argument");
+        set_error("%s: null pointer argument", who);
         return MOCO_ERR_INVALID;
     }
     if (N <= 0 || C <= 0 || K <= 0 || !(inv_T > 0.f) || (qk_dtype != MOCO_F32 && qk_dtype != MOCO_BF16)) {
-        set_error("moco_nce_fwd: bad N/C/K/inv_T/dtype (N=%d C=%d K=%d inv_T=%g dtype=%d)", N, C, K, (double)inv_T, qk_dtype);
+        set_error("%s: bad N/C/K/inv_T/dtype (N=%d C=%d K=%d inv_T=%g dtype=%d)", who, N, C, K, (double)inv_T, qk_dtype);
         return MOCO_ERR_INVALID;
     }
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
-        set_error("moco_nce_fwd: workspace must be 256-byte aligned");
+        set_error("%s: workspace must be 256-byte aligned", who);
         return MOCO_ERR_INVALID;
     }
     NceWorkspace ws = carve_workspace(workspace, N, C);
     if (workspace_bytes < ws.bytes) {
-        set_error("moco_nce_fwd: workspace too small (%zu < %zu)", workspace_bytes, ws.bytes);
+        set_error("%s: workspace too small (%zu < %zu)", who, workspace_bytes, ws.bytes);
         return MOCO_ERR_WORKSPACE;
     }
     DevInfo d = device_info();
-    if (!d.ok) { set_error("moco_nce_fwd: no CUDA device"); return MOCO_ERR_CUDA; }
-
-    cudaError_t e = launch_prep(q, k, qk_dtype, N, C, ws, stream);
-    if (e != cudaSuccess) return cuda_fail("prep kernel", e);
-    const __nv_bfloat16* qb = qk_dtype == MOCO_BF16 ? static_cast<const __nv_bfloat16*>(q) : ws.q_bf16;
+    if (!d.ok) { set_error("%s: no CUDA device", who); return MOCO_ERR_CUDA; }
     const __nv_bfloat16* queue = static_cast<const __nv_bfloat16*>(queue_bf16);
-
-    const bool tc_shape = (C % 64 == 0) && C <= 256 && ((reinterpret_cast<uintptr_t>(qb) & 15) == 0) &&
-                          ((reinterpret_cast<uintptr_t>(queue) & 15) == 0);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(q) & 15) == 0) && ((reinterpret_cast<uintptr_t>(queue) & 15) == 0);
+    const bool tc_shape = (C % 64 == 0) && C <= 256 && aligned;
     const bool want_tc = !(flags & MOCO_NCE_FORCE_SIMT);
     if ((flags & (MOCO_NCE_CTA_PAIR | MOCO_NCE_SINGLE_CTA)) && (!tc_shape || d.major != 10)) {
-        set_error("moco_nce_fwd: tcgen05 path requested but unavailable (C=%d, sm_%d%d)", C, d.major, d.minor);
+        set_error("%s: tcgen05 path requested but unavailable (C=%d, sm_%d%d)", who, C, d.major, d.minor);
         return MOCO_ERR_UNSUPPORTED;
     }
+    cudaError_t e;
+    bool prepped = false;
+    // ---- one sweep over the queue for loss + gradient, then ONE tail kernel (merge, dq, optional enqueue)
+    const bool one_pass = want_tc && tc_shape && d.major == 10 && dq && !logits && !(flags & MOCO_NCE_TWO_PASS) &&
+                          ((flags & MOCO_NCE_ONE_PASS) || inv_T <= MOCO_ONE_PASS_MAX_INV_T) &&
+                          !(normalize && C > 128);
+    if (one_pass) {
+        const __nv_bfloat16* qb = static_cast<const __nv_bfloat16*>(q);
+        if (C > 128 && qk_dtype == MOCO_F32) {            // the C > 128 kernel reads a bf16 copy of q
+            e = launch_prep(q, k, qk_dtype, N, C, ws, stream);
+            if (e != cudaSuccess) return cuda_fail("prep kernel", e);
+            prepped = true;
+            qb = ws.q_bf16;
+        }
+        int slices = 0, n_pad = 0;
+        prof_mark(MOCO_PROF_DQ, 0, stream);
+        e = launch_sweep(q, qk_dtype, normalize, qb, queue, N, C, K, inv_T, nullptr, d.sms, &slices, &n_pad, ws, stream);
+        prof_mark(MOCO_PROF_DQ, 1, stream);
+        if (e == cudaSuccess) {
+            const bool fuse_enq = enq.n_all > 0 && nce_tail_can_enqueue(C, normalize);
+            e = launch_nce_tail(N, C, K, slices, n_pad, inv_T, q, k, qk_dtype, normalize, queue, lse, loss_rows, prob_rows,
+                                loss_prob, dq, ws, static_cast<__nv_bfloat16*>(enq.queue_bf16), enq.queue_f32, enq.k_all,
+                                enq.k_dtype, fuse_enq ? enq.n_all : 0, enq.index, enq.index_dev, 0, K, stream);
+            if (e != cudaSuccess) return cuda_fail("tail kernel", e);
+            if (enq.n_all > 0 && !fuse_enq) {
+                e = launch_enqueue(static_cast<__nv_bfloat16*>(enq.queue_bf16), enq.queue_f32, enq.k_all, enq.k_dtype,
+                                   enq.n_all, C, K, enq.index, 0, K, stream);
+                if (e != cudaSuccess) return cuda_fail("enqueue kernel", e);
+            }
+            return MOCO_OK;
+        }
+        if (e != cudaErrorNotSupported) return cuda_fail("tcgen05 one-sweep kernel", e);
+        // shape outside the one-sweep kernels' envelope: two-pass below
+    }
+    if (normalize || enq.index_dev) {
+        set_error("%s: in-kernel normalisation / device-side ring index need the one-sweep path "
+                  "(C in {64, 128}, gradient requested, no dense logits, inv_T <= %g)", who, (double)MOCO_ONE_PASS_MAX_INV_T);
+        return MOCO_ERR_UNSUPPORTED;
+    }
+    if (!prepped) {
+        e = launch_prep(q, k, qk_dtype, N, C, ws, stream);
+        if (e != cudaSuccess) return cuda_fail("prep kernel", e);
+    }
+    const __nv_bfloat16* qb = qk_dtype == MOCO_BF16 ? static_cast<const __nv_bfloat16*>(q) : ws.q_bf16;
+    auto finish = [&]() -> int {                       // the enqueue of moco_nce_step on the non-fused paths
+        if (enq.n_all > 0) {
+            cudaError_t ee = launch_enqueue(static_cast<__nv_bfloat16*>(enq.queue_bf16), enq.queue_f32, enq.k_all,
+                                            enq.k_dtype, enq.n_all, C, K, enq.index, 0, K, stream);
+            if (ee != cudaSuccess) return cuda_fail("enqueue kernel", ee);
+        }
+        return MOCO_OK;
+    };
     if (want_tc && tc_shape && d.major == 10) {
         NceTcParams p;
         p.q_bf16 = qb; p.queue = queue; p.N = N; p.C = C; p.K = K; p.inv_T = inv_T; p.logits = logits;
         p.cta_group = (flags & MOCO_NCE_CTA_PAIR) ? 2 : 1;
         p.num_sms = d.sms;
         p.slices = 0; p.n_pad = 0;
-        // one sweep over the queue for loss + gradient when that is numerically safe (include/moco_b200.h)
-        const bool one_pass = dq && !logits && !(flags & MOCO_NCE_TWO_PASS) &&
-                              ((flags & MOCO_NCE_ONE_PASS) || inv_T <= MOCO_ONE_PASS_MAX_INV_T);
-        if (one_pass) {
-            int slices = 0, n_pad = 0;
-            prof_mark(MOCO_PROF_DQ, 0, stream);
-            e = launch_nce_dq2_tc(qb, queue, N, C, K, inv_T, nullptr, d.sms, &slices, &n_pad, ws, stream);
-            prof_mark(MOCO_PROF_DQ, 1, stream);
-            if (e == cudaSuccess) {
-                e = launch_combine(N, C, slices, n_pad, inv_T, nullptr, K, lse, loss_rows, prob_rows, loss_prob, ws, stream);
-                if (e != cudaSuccess) return cuda_fail("combine kernel", e);
-                e = launch_dq_reduce(N, C, slices, n_pad, inv_T, k, qk_dtype, prob_rows, dq, ws.part_o, stream,
-                                     ws.part_ms, lse);
-                if (e != cudaSuccess) return cuda_fail("dq reduce kernel", e);
-                return MOCO_OK;
-            }
-            if (e != cudaErrorNotSupported) return cuda_fail("tcgen05 one-pass kernel", e);
-            // shape outside the one-pass kernel's envelope: two-pass below
-        }
         prof_mark(MOCO_PROF_STATS, 0, stream);
         e = launch_nce_tc(p, ws, stream);
         prof_mark(MOCO_PROF_STATS, 1, stream);
@@ -145,13 +192,13 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
             if (dq) {
                 int slices = 0, n_pad = 0;
                 prof_mark(MOCO_PROF_DQ, 0, stream);
-                e = launch_nce_dq2_tc(qb, queue, N, C, K, inv_T, lse, d.sms, &slices, &n_pad, ws, stream);
+                e = launch_sweep(qb, MOCO_BF16, 0, qb, queue, N, C, K, inv_T, lse, d.sms, &slices, &n_pad, ws, stream);
                 prof_mark(MOCO_PROF_DQ, 1, stream);
                 if (e != cudaSuccess) return cuda_fail("tcgen05 dq kernel", e);
                 e = launch_dq_reduce(N, C, slices, n_pad, inv_T, k, qk_dtype, prob_rows, dq, ws.part_o, stream);
                 if (e != cudaSuccess) return cuda_fail("dq reduce kernel", e);
             }
-            return MOCO_OK;
+            return finish();
         }
         if (e != cudaErrorNotSupported || (flags & (MOCO_NCE_CTA_PAIR | MOCO_NCE_SINGLE_CTA)))
             return cuda_fail("tcgen05 stats kernel", e);
@@ -159,7 +206,34 @@ int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_b
     }
     e = launch_simt_rows(qb, k, qk_dtype, queue, N, C, K, inv_T, logits, lse, loss_rows, prob_rows, loss_prob, dq, ws, stream);
     if (e != cudaSuccess) return cuda_fail("generic NCE kernel", e);
-    return MOCO_OK;
+    return finish();
+}
+
+extern "C" {
+
+int moco_nce_fwd(const void* q, const void* k, int qk_dtype, const void* queue_bf16, int N, int C, int K,
+                 float inv_T, float* logits, float* lse, float* loss_rows, float* prob_rows, float* loss_prob,
+                 float* dq, void* workspace, size_t workspace_bytes, int flags, void* stream_) {
+    const EnqueueSpec none = {nullptr, nullptr, nullptr, 0, 0, 0, nullptr};
+    return nce_head(q, k, qk_dtype, 0, queue_bf16, N, C, K, inv_T, logits, lse, loss_rows, prob_rows, loss_prob, dq,
+                    workspace, workspace_bytes, flags, none, static_cast<cudaStream_t>(stream_), "moco_nce_fwd");
+}
+
+int moco_nce_step(const void* q, const void* k, int qk_dtype, int normalize, void* queue_bf16, float* queue_f32,
+                  int N, int C, int K, float inv_T, const void* k_all, int k_all_dtype, int n_all, int64_t index,
+                  int64_t* index_dev, float* lse, float* loss_rows, float* prob_rows, float* loss_prob, float* dq,
+                  void* workspace, size_t workspace_bytes, int flags, void* stream_) {
+    if (!k_all || n_all < 0 || n_all > K || (k_all_dtype != MOCO_F32 && k_all_dtype != MOCO_BF16) ||
+        (!index_dev && (index < 0 || index >= K))) {
+        g_err[0] = 0;
+        set_error("moco_nce_step: bad enqueue argument (n_all=%d K=%d index=%lld)", n_all, K, (long long)index);
+        return MOCO_ERR_INVALID;
+    }
+    const EnqueueSpec enq = {queue_bf16, queue_f32, k_all, k_all_dtype, n_all, (long long)index,
+                             reinterpret_cast<long long*>(index_dev)};
+    return nce_head(q, k, qk_dtype, normalize ? 1 : 0, queue_bf16, N, C, K, inv_T, nullptr, lse, loss_rows, prob_rows,
+                    loss_prob, dq, workspace, workspace_bytes, flags, enq, static_cast<cudaStream_t>(stream_),
+                    "moco_nce_step");
 }
 
 int moco_prof_set_events(int kernel, void* ev_start, void* ev_stop) {
@@ -254,7 +328,7 @@ int moco_nce_shard_stats(const void* q_all, const void* k_all, int qk_dtype, con
     if (flags & MOCO_NCE_ONE_PASS) {
         // one sweep over the shard: (stabiliser, sum) partials for the cross-rank merge AND the unnormalised
         // P~.Queue partials, which stay in the workspace until moco_nce_shard_dq(..., MOCO_NCE_ONE_PASS) rescales them
-        e = launch_nce_dq2_tc(p.q_bf16, p.queue, N, C, Ks, inv_T, nullptr, d.sms, &p.slices, &p.n_pad, ws, stream);
+        e = launch_sweep(q_all, qk_dtype, 0, p.q_bf16, p.queue, N, C, Ks, inv_T, nullptr, d.sms, &p.slices, &p.n_pad, ws, stream);
         if (e != cudaSuccess) return cuda_fail("tcgen05 one-pass kernel", e);
     } else {
         e = launch_nce_tc(p, ws, stream);
@@ -296,14 +370,15 @@ int moco_nce_shard_dq(const void* q_all, int q_dtype, const void* shard_bf16, co
     if (flags & MOCO_NCE_ONE_PASS) {
         // the sweep already happened in moco_nce_shard_stats(..., MOCO_NCE_ONE_PASS) on this workspace: only the
         // slice count is needed, then O = sum_s 2^(m_s - lse) O~_s
-        e = launch_nce_dq2_tc(qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, nullptr, d.sms,
-                              &slices, &n_pad, ws, stream, /*plan_only=*/true);
+        e = launch_sweep(q_all, q_dtype, 0, qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, nullptr, d.sms,
+                         &slices, &n_pad, ws, stream, /*plan_only=*/true);
         if (e != cudaSuccess) return cuda_fail("one-pass plan", e);
         e = launch_dq_reduce(N, C, slices, n_pad, inv_T, nullptr, 0, nullptr, o_partial, ws.part_o, stream, ws.part_ms, lse_all);
         if (e != cudaSuccess) return cuda_fail("dq reduce kernel", e);
         return MOCO_OK;
     }
-    e = launch_nce_dq2_tc(qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, lse_all, d.sms, &slices, &n_pad, ws, stream);
+    e = launch_sweep(q_all, q_dtype, 0, qb, static_cast<const __nv_bfloat16*>(shard_bf16), N, C, Ks, inv_T, lse_all, d.sms, &slices,
+                     &n_pad, ws, stream);
     if (e != cudaSuccess) return cuda_fail("tcgen05 dq kernel", e);
     e = launch_dq_reduce(N, C, slices, n_pad, inv_T, nullptr, 0, nullptr, o_partial, ws.part_o, stream);
     if (e != cudaSuccess) return cuda_fail("dq reduce kernel", e);

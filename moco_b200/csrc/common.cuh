@@ -116,6 +116,17 @@ cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* 
                               float inv_T, const float* lse, int num_sms, int* slices_out,
                               int* n_pad_out, const NceWorkspace& ws, cudaStream_t stream, bool plan_only = false);
 
+// one-sweep head for C in {64, 128} (nce_head128_sm100.cu) and the fused tail (nce_tail.cu)
+cudaError_t launch_nce_head128(const void* q, int q_dtype, int normalize, const __nv_bfloat16* queue, int N, int C, int K,
+                               float inv_T, const float* lse, int num_sms, int* slices_out, int* n_pad_out,
+                               const NceWorkspace& ws, cudaStream_t stream, bool plan_only = false);
+bool nce_tail_can_enqueue(int C, int normalize);
+cudaError_t launch_nce_tail(int N, int C, int K, int slices, int n_pad, float inv_T, const void* q, const void* k,
+                            int qk_dtype, int normalize, const __nv_bfloat16* queue, float* lse, float* loss_rows,
+                            float* prob_rows, float* loss_prob, float* dq, const NceWorkspace& ws,
+                            __nv_bfloat16* enq_bf16, float* enq_f32, const void* k_all, int k_all_dtype, int n_all,
+                            long long index, long long* index_dev, long long row0, long long nrows, cudaStream_t stream);
+
 void set_error(const char* fmt, ...);
 
 }  // namespace moco

@@ -452,11 +452,11 @@ cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* 
                               float inv_T, const float* lse, int num_sms, int* slices_out,
                               int* n_pad_out, const NceWorkspace& ws, cudaStream_t stream, bool plan_only) {
     const bool fused = (lse == nullptr);
-    if (C % 64 != 0 || C < 64 || C > 256) return cudaErrorNotSupported;
+    if (C != 192 && C != 256) return cudaErrorNotSupported;      // C <= 128 runs on nce_head128_sm100.cu
     const int kchunks = C / 64;
     const int mblks = (N + 127) / 128;
     if (mblks > num_sms) return cudaErrorNotSupported;
-    const int BN = (C <= 128) ? 128 : 64;
+    const int BN = 64;
     const int num_tiles = (K + BN - 1) / BN;
     const int n_pad = mblks * 128;
     *n_pad_out = n_pad;
@@ -490,7 +490,6 @@ cudaError_t launch_nce_dq2_tc(const __nv_bfloat16* q_bf16, const __nv_bfloat16* 
                                mblks, num_tiles, n_pad, slices_out, stream, tm_queue, tm_queue, a, fill, true,     \
                                plan_only);                                                                         \
     } while (0)
-    if (BN == 128) MOCO_DQ2_LAUNCH(128, 0);
     MOCO_DQ2_LAUNCH(64, 1);
 #undef MOCO_DQ2_LAUNCH
 }

@@ -1,0 +1,429 @@
+// InfoNCE head kernel for feat_dim <= 128 (MoCo's 128): ONE sweep over the queue on tcgen05 produces the softmax
+// statistics AND the unnormalised gradient partials of a 128-row block of queries against a slice of the queue.
+//
+//   q[128, C]   read straight from the caller's tensor (fp32 or bf16, optionally L2-normalised here -- the
+//               reference's Normalize layer, moco/models/resnet.py:24-33 -- then rounded to bf16) by all 16 softmax
+//               warps with coalesced row loads and written into shared memory in the UMMA K-major / 128B-swizzle
+//               layout: no separate cast kernel, no global round trip, nothing for this kernel to wait on but q.
+//   S[128, 128] = q . tile^T          tcgen05.mma, A and B from shared memory, fp32 accumulators in TMEM,
+//                                     THREE S/P buffers (TMEM: O [0,128) | S0 S1 S2 at 128 + 128 b)
+//   P           = 2^(S log2e/T - m)   softmax warps: tcgen05.ld -> ex2 -> bf16 pairs -> tcgen05.st over the start of
+//                                     each thread's OWN S columns (no cross-thread hazard)
+//   O[128, C]  += P . tile            tcgen05.mma with P as the TMEM-resident A operand and the SAME smem tile as
+//                                     MN-major B; O stays in TMEM for the whole slice
+//
+// Why three S buffers: with two, the per-buffer dependency chain S(i) -> softmax(i) -> P.V(i) -> S(i+2) is exactly
+// as long as two tiles of tensor work, so every latency in it (commit -> mbarrier wake-up, tcgen05.ld/st, the
+// issuing thread's ~65 cycles per MMA) was exposed: 1,750 cycles per 128-row tile against 1,024 of tensor / MUFU
+// work (profiles/r2a_trace_c3.txt).  q used to live in TMEM (64 columns); staging it in shared memory instead makes
+// room for the third buffer, so S(i+2) is already waiting when the softmax group finishes tile i.
+//
+// Two MMA-issuing threads: a tcgen05.mma costs its issuing thread ~65-80 cycles, so the 8 S + 8 P.V MMAs of a tile
+// keep ONE thread busy ~1,500-1,850 cycles per tile (profiles/r2b_trace_c4.txt) -- more than the 1,024 cycles of
+// tensor work.  Warp 1 issues S, warp 3 issues P.V; S(i+3) overwriting the buffer P.V(i) reads P from is ordered by
+// the s_free mbarrier P.V(i)'s tcgen05.commit arrives on.
+//
+// Stabiliser (FUSED = true, no lse yet): m_i = (log2e / T) * |q_i|, computed from the row while it is staged -- an
+// upper bound of every logit of the row against unit-norm queue rows, so no pass over the first S tile is needed to
+// find a maximum (that pre-pass cost every CTA ~700 cycles of its critical path).  P~ = 2^(x - m), l = sum P~,
+// O~ = sum P~ queue_j; the tail kernel (nce_tail.cu) merges the per-slice (m, l) pairs and rescales each slice's O~
+// by 2^(m - lse).  All terms of a row share the exponent offset, so precision is that of the exponent-free bf16 / fp32
+// formats; what can go wrong is only the exponent RANGE (queue rows far above unit norm: overflow; logits far below
+// the bound, e.g. un-normalised q: everything flushes to zero).  The tail kernel detects both (l > 2^100 or the total
+// < 2^-80) and recomputes such rows exactly, so the result is never silently wrong.
+// FUSED = false: P is normalised with the given lse (two-pass mode, after the statistics kernel).
+//
+// Replaces torch.mm + cat + div + CrossEntropyLoss + softmax and autograd's backward GEMM with its queue clone
+// (moco/NCE/Contrast.py:23-27, NCECriterion.py:11-13, train.py:264,273).
+#include <cuda.h>
+
+#include "../../include/moco_b200.h"
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+#include "tc_common.cuh"
+
+namespace moco {
+
+#ifdef MOCO_TRACE
+__device__ long long g_h128_trace[4][64][8];
+#define MOCO_TR(role, tile, slot) do { if (blockIdx.x == 0 && (tile) < 64) g_h128_trace[role][tile][slot] = clock64(); } while (0)
+#else
+#define MOCO_TR(role, tile, slot) do { } while (0)
+#endif
+
+constexpr int kH1Threads = 640;           // warp0 TMA, warp1 S-MMA, warp2 TMEM alloc, warp3 PV-MMA, warps 4-19 softmax
+constexpr int kH1BN = 128;                // queue rows per tile
+constexpr int kH1Bufs = 3;                // S/P buffers in TMEM
+constexpr uint32_t kH1OCol = 0, kH1SCol = 128;
+constexpr int kH1Slab = kH1BN * 128;      // one [128 rows x 64 bf16] swizzled slab
+
+struct Head128Args {
+    int N, C, K;
+    int mblks, slices, n_pad, num_tiles, stages;
+    float inv_T;
+    const void* q;            // [N, C] fp32 or bf16 (qk_dtype)
+    int q_dtype;
+    int normalize;            // 1: L2-normalise each q row before the bf16 rounding
+    const float* lse;         // [N] natural log (two-pass mode)
+    float* part_o;            // [slices, n_pad, C]
+    float2* part_ms;          // [slices, n_pad] (stabiliser, sum) in the log2 domain (one-sweep mode)
+    unsigned int* counters;   // workspace counters the tail kernel's last-block logic uses: zeroed here
+};
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kH1Threads, 1)
+nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_constant__ CUtensorMap tm_unused,
+                   const Head128Args a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+    if (threadIdx.x == 0) MOCO_TR(3, 0, 0);
+    const int kchunks = a.C >> 6;
+    const int NS = a.stages;
+    const int tile_bytes = kchunks * kH1Slab;
+    uint8_t* q_s = smem;                                   // kchunks slabs of [128 rows x 128 B]
+    uint8_t* v_s = q_s + tile_bytes;                       // NS queue tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + (size_t)NS * tile_bytes);
+    uint64_t* kv_full = bars;
+    uint64_t* kv_empty = bars + NS;
+    uint64_t* s_full = bars + 2 * NS;                      // [3]
+    uint64_t* p_full = bars + 2 * NS + 3;                  // [3]
+    uint64_t* o_full = bars + 2 * NS + 6;
+    uint64_t* q_ready = bars + 2 * NS + 7;
+    uint64_t* s_free = bars + 2 * NS + 8;                  // [3]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 11);
+    float* exch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);     // [3][128] floats
+    float* mrow = exch + 2 * kRowsPerCta;      // [128] row stabilisers: read once at the start; the slot is reused for the final sums
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mblk = blockIdx.x % a.mblks;
+    const int slice = blockIdx.x / a.mblks;
+    const int t0 = (int)(((long long)slice * a.num_tiles) / a.slices);
+    const int t1 = (int)(((long long)(slice + 1) * a.num_tiles) / a.slices);
+    const int ntiles = t1 - t0;
+    const int row0 = mblk * kRowsPerCta;
+
+    pdl_launch_dependents();
+    // ---- set-up that touches no global memory (overlaps the predecessor kernel under PDL) ----
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_queue);
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int b = 0; b < kH1Bufs; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); mbar_init(&s_free[b], 1); }
+        mbar_init(o_full, 1);
+        mbar_init(q_ready, 16);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<1>(tmem_slot, 512);
+        tmem_relinquish<1>();
+    }
+    pdl_wait();                                            // predecessor complete: q / lse / the queue are final
+    if (blockIdx.x == 0 && threadIdx.x < 4 && a.counters != nullptr) a.counters[threadIdx.x] = 0u;
+    // q rows of this block: 16 warps x 8 rows, one coalesced row load per (warp, row), all 8 in flight before the
+    // set-up barrier (their latency is the kernel's critical path at small K)
+    if (threadIdx.x == 0) MOCO_TR(3, 0, 1);
+    // RAW bits only: nothing may consume a loaded value before the barrier below, or the load latency lands in front of it
+    uint4 qraw[8];
+    const int epl = a.C >> 5;                              // elements per lane: 2 (C = 64) or 4 (C = 128)
+    const int qbytes = epl * (a.q_dtype == MOCO_F32 ? 4 : 2);   // bytes per lane per row: 4, 8 or 16
+    if (warp >= 4) {
+        const int sw = warp - 4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int grow = row0 + sw * 8 + j;
+            const int srow = grow < a.N ? grow : 0;        // clamped: padding rows are zeroed when they are staged
+            const uint8_t* src = static_cast<const uint8_t*>(a.q) + ((size_t)srow * a.C + lane * epl) * (a.q_dtype == MOCO_F32 ? 4 : 2);
+            qraw[j] = make_uint4(0u, 0u, 0u, 0u);
+            if (qbytes == 16)     qraw[j] = __ldg(reinterpret_cast<const uint4*>(src));
+            else if (qbytes == 8) { const uint2 u = __ldg(reinterpret_cast<const uint2*>(src)); qraw[j].x = u.x; qraw[j].y = u.y; }
+            else                  qraw[j].x = __ldg(reinterpret_cast<const uint32_t*>(src));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) MOCO_TR(3, 0, 2);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer (queue tiles)
+            int st = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < ntiles; ++i, st = (st + 1 == NS) ? 0 : st + 1, ph ^= (st == 0) ? 1u : 0u) {
+                mbar_wait(&kv_empty[st], ph ^ 1u);
+                mbar_arrive_expect_tx(&kv_full[st], (uint32_t)tile_bytes);
+                for (int kc = 0; kc < kchunks; ++kc)
+                    tma_load_2d(&tm_queue, &kv_full[st], v_s + (size_t)st * tile_bytes + kc * kH1Slab, kc * 64,
+                                (t0 + i) * kH1BN);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer 1 of 2: S = q . tile^T (both operands in smem)
+            const uint32_t idesc_s = make_idesc_bf16(128, kH1BN, 0, 0);
+            mbar_wait(q_ready, 0);
+            tc_fence_after();
+            MOCO_TR(3, 1, 0);
+            const uint64_t q_desc0 = make_sw128_desc(smem_u32(q_s), 0, 1024);
+            const uint64_t vk_desc0 = make_sw128_desc(smem_u32(v_s), 0, 1024);           // tile as K-major B
+            constexpr uint64_t kSlabUnits = (uint64_t)(kH1Slab >> 4);
+            const uint64_t tile_units = (uint64_t)(tile_bytes >> 4);
+            int s_st = 0; uint32_t s_ph = 0; uint64_t s_vdesc = vk_desc0; uint32_t s_b = 0, s_use = 0;
+            for (int i = 0; i < ntiles; ++i) {
+                MOCO_TR(0, i, 4);
+                mbar_wait(&kv_full[s_st], s_ph);
+                if (s_use > 0) mbar_wait(&s_free[s_b], (s_use - 1u) & 1u);      // P.V(i-3) has consumed P in buffer s_b
+                tc_fence_after();
+                MOCO_TR(0, i, 5);
+                const uint32_t d = tmem_base + kH1SCol + s_b * (uint32_t)kH1BN;
+                uint64_t qd = q_desc0, vd = s_vdesc;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    umma_ss<1>(d, qd, vd, idesc_s, (uint32_t)(kc != 0));
+                    umma_ss<1>(d, qd + 2, vd + 2, idesc_s, 1u);
+                    umma_ss<1>(d, qd + 4, vd + 4, idesc_s, 1u);
+                    umma_ss<1>(d, qd + 6, vd + 6, idesc_s, 1u);
+                    qd += kSlabUnits;
+                    vd += kSlabUnits;
+                }
+                MOCO_TR(0, i, 6);
+                umma_commit<1>(&s_full[s_b]);
+                MOCO_TR(0, i, 7);
+                s_vdesc += tile_units;
+                if (++s_st == NS) { s_st = 0; s_ph ^= 1u; s_vdesc = vk_desc0; }
+                if (++s_b == kH1Bufs) { s_b = 0; ++s_use; }
+            }
+        }
+    } else if (warp == 3) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer 2 of 2: O += P . tile (P in TMEM, tile MN-major)
+            const uint32_t idesc_o = make_idesc_bf16(128, (uint32_t)a.C, 0, 1);
+            const uint64_t vm_desc0 = make_sw128_desc(smem_u32(v_s), kH1Slab, 1024);
+            const uint64_t tile_units = (uint64_t)(tile_bytes >> 4);
+            int o_st = 0; uint32_t o_kph = 0; uint64_t o_vdesc = vm_desc0; uint32_t o_b = 0, o_ph = 0;
+            for (int i = 0; i < ntiles; ++i) {
+                MOCO_TR(0, i, 0);
+                mbar_wait(&p_full[o_b], o_ph);
+                mbar_wait(&kv_full[o_st], o_kph);         // complete long ago (S(i) read the tile); observed for visibility
+                tc_fence_after();
+                MOCO_TR(0, i, 1);
+#pragma unroll
+                for (int kk = 0; kk < kH1BN / 16; ++kk) {
+                    // P rows [16kk, 16kk+16) of the tile: column half hh wrote them at the start of ITS S columns
+                    const uint32_t hh = (uint32_t)(kk >> 2), off = (uint32_t)((kk & 3) * 8);
+                    umma_ts<1>(tmem_base + kH1OCol, tmem_base + kH1SCol + o_b * (uint32_t)kH1BN + hh * 64u + off,
+                               o_vdesc + (uint64_t)(kk * 128), idesc_o, (uint32_t)((i | kk) != 0));
+                }
+                MOCO_TR(0, i, 2);
+                umma_commit<1>(&kv_empty[o_st]);
+                if (i + kH1Bufs < ntiles) umma_commit<1>(&s_free[o_b]);
+                MOCO_TR(0, i, 3);
+                o_vdesc += tile_units;
+                if (++o_st == NS) { o_st = 0; o_kph ^= 1u; o_vdesc = vm_desc0; }
+                if (++o_b == kH1Bufs) { o_b = 0; o_ph ^= 1u; }
+            }
+            umma_commit<1>(o_full);
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------- softmax warps (16): q staging, softmax, O epilogue
+        const int sw = warp - 4;
+        const int quarter = warp & 3;                     // TMEM lanes [32 * quarter, +32)
+        const int chalf = (sw >> 2) & 1;
+        const int grp = sw >> 3;                          // tile parity this warp serves
+        const int row_local = quarter * 32 + lane;
+        const int grow = row0 + row_local;
+        const float scale2 = a.inv_T * kLog2e;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        {
+            // q rows sw*8 .. sw*8+7 -> shared memory, K-major 128B-swizzle (row r at r*128 B inside a 64-column slab,
+            // 16-byte chunk c at position c ^ (r & 7)): exactly what a TMA load of the bf16 tensor would have written
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = sw * 8 + j;
+                float v0, v1, v2 = 0.f, v3 = 0.f;
+                if (a.q_dtype == MOCO_F32) {
+                    v0 = __uint_as_float(qraw[j].x); v1 = __uint_as_float(qraw[j].y);
+                    if (epl == 4) { v2 = __uint_as_float(qraw[j].z); v3 = __uint_as_float(qraw[j].w); }
+                } else {
+                    const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qraw[j].x));
+                    v0 = lo.x; v1 = lo.y;
+                    if (epl == 4) {
+                        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qraw[j].y));
+                        v2 = hi.x; v3 = hi.y;
+                    }
+                }
+                if (j == 0 && sw == 0 && lane == 0) MOCO_TR(3, 0, 3);     // first q data in registers
+                if (row0 + r >= a.N) { v0 = v1 = v2 = v3 = 0.f; }
+                float ss = v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                float nrm = sqrtf(ss);
+                if (a.normalize) {
+                    v0 = v0 / nrm; v1 = v1 / nrm; v2 = v2 / nrm; v3 = v3 / nrm;      // x / sqrt(sum x^2): resnet.py:31-32
+                    if (row0 + r >= a.N) { v0 = v1 = v2 = v3 = 0.f; }                // padding rows: 0/0 must not reach the MMA
+                    nrm = 1.f;
+                }
+                if (lane == 0) mrow[r] = nrm * a.inv_T * kLog2e;                     // the row's stabiliser (one-sweep mode)
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1);
+                if (epl == 4) {
+                    const __nv_bfloat162 hi = __floats2bfloat162_rn(v2, v3);
+                    const int col = lane * 4;
+                    uint8_t* dst = q_s + (col >> 6) * kH1Slab + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) + (col & 7) * 2;
+                    *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo),
+                                                                *reinterpret_cast<const uint32_t*>(&hi));
+                } else {
+                    const int col = lane * 2;
+                    uint8_t* dst = q_s + r * 128 + (((col >> 3) ^ (r & 7)) << 4) + (col & 7) * 2;
+                    *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(&lo);
+                }
+            }
+            fence_proxy_async();                          // generic-proxy smem writes -> visible to tcgen05.mma
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_ready);
+            if (sw == 0 && lane == 0) MOCO_TR(3, 0, 4);
+        }
+        constexpr int kHalf = kH1BN / 2;                  // 64 S columns per thread, in two 32-column chunks
+        const bool ragged = (a.K % kH1BN) != 0;
+        float lse2 = (!FUSED && grow < a.N) ? a.lse[grow] * kLog2e : 0.f;
+        float lsum = 0.f;
+        if (FUSED) {
+            named_bar_sync(1, 16 * 32);                   // every softmax warp has staged its rows: mrow[] is complete
+            lse2 = mrow[row_local];
+        }
+        const bool tracer = (quarter == 0 && chalf == 0 && lane == 0);
+        uint32_t b = (uint32_t)grp;                       // buffer of tile i = i % 3, advanced by 2 per iteration
+        uint32_t use = 0;                                 // i / 3
+        for (int i = grp; i < ntiles; i += 2) {
+            if (tracer) MOCO_TR(1 + grp, i, 0);
+            mbar_wait(&s_full[b], use & 1u);
+            tc_fence_after();
+            if (tracer) MOCO_TR(1 + grp, i, 1);
+            const uint32_t own = lane_base + kH1SCol + b * (uint32_t)kH1BN + (uint32_t)(chalf * kHalf);
+            const int col0 = (t0 + i) * kH1BN + chalf * kHalf;
+            const int valid = (ragged && t0 + i == a.num_tiles - 1) ? (a.K - col0) : kHalf;
+#pragma unroll
+            for (int h = 0; h < kHalf / 32; ++h) {
+                uint32_t r[32];
+                tmem_ld32(own + (uint32_t)(h * 32), r);
+                tmem_ld_wait();
+                if (tracer && h == 0) MOCO_TR(1 + grp, i, 2);
+                float e[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) e[j] = ex2(fmaf(__uint_as_float(r[j]), scale2, -lse2));
+                if (FUSED && valid < kHalf) {             // ragged last tile only: mask (also keeps inf * 0 out of O)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (h * 32 + j >= valid) e[j] = 0.f;
+                }
+                uint32_t p[16];
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    if (FUSED) { s0 += e[j]; s1 += e[j + 1]; }
+                    __nv_bfloat162 hh = __floats2bfloat162_rn(e[j], e[j + 1]);
+                    p[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                }
+                if (FUSED) lsum += s0 + s1;
+                if (tracer && h == 0) MOCO_TR(1 + grp, i, 3);
+                tmem_st16(own + (uint32_t)(h * 16), p);
+            }
+            if (tracer) MOCO_TR(1 + grp, i, 4);
+            tmem_st_wait();
+            if (tracer) MOCO_TR(1 + grp, i, 5);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[b]);
+            if (tracer) MOCO_TR(1 + grp, i, 6);
+            b += 2;
+            if (b >= (uint32_t)kH1Bufs) { b -= (uint32_t)kH1Bufs; ++use; }
+        }
+        if (FUSED) {
+            const int part = grp * 2 + chalf;
+            named_bar_sync(1, 16 * 32);                   // every thread has long read mrow[]: its slot becomes exch[2]
+            if (part > 0) exch[(part - 1) * kRowsPerCta + row_local] = lsum;
+            named_bar_sync(2 + quarter, 128);
+            if (part == 0)
+                a.part_ms[(size_t)slice * a.n_pad + grow] =
+                    make_float2(lse2, ((lsum + exch[row_local]) + exch[kRowsPerCta + row_local]) + exch[2 * kRowsPerCta + row_local]);
+        }
+        // O epilogue: C/4 columns per warp of a lane quarter when that is a multiple of 32, else C/2 on group 0
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        if (sw == 0 && lane == 0) MOCO_TR(3, 0, 5);
+        const bool four = (a.C & 127) == 0;
+        if (four || grp == 0) {
+            const int ccols = four ? (a.C >> 2) : (a.C >> 1);
+            const int cbeg = (four ? (grp * 2 + chalf) : chalf) * ccols;
+            // each 32 x 32 block goes through a padded (stride 33) buffer in the now idle tile ring, then out as
+            // 128-byte rows (a direct store would hit 32 rows 512 B apart per instruction)
+            float* tbuf = reinterpret_cast<float*>(v_s) + sw * (32 * 33);
+            float* oblk = a.part_o + ((size_t)slice * a.n_pad + row0 + quarter * 32) * a.C + cbeg + lane;
+            for (int c = 0; c < ccols; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(lane_base + kH1OCol + (uint32_t)(cbeg + c), r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+                __syncwarp();
+#pragma unroll
+                for (int k2 = 0; k2 < 32; ++k2) oblk[(size_t)k2 * a.C + c] = tbuf[k2 * 33 + lane];
+                __syncwarp();
+            }
+        }
+    }
+
+    if (warp == 4 && lane == 0) MOCO_TR(3, 0, 6);
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) MOCO_TR(3, 0, 7);
+    if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
+// lse == nullptr selects the one-sweep mode (the kernel also writes ws.part_ms).
+// plan_only: launch nothing, just report the slice count / padded rows this shape gets.
+cudaError_t launch_nce_head128(const void* q, int q_dtype, int normalize, const __nv_bfloat16* queue, int N, int C, int K,
+                               float inv_T, const float* lse, int num_sms, int* slices_out, int* n_pad_out,
+                               const NceWorkspace& ws, cudaStream_t stream, bool plan_only) {
+    const bool fused = (lse == nullptr);
+    if (C != 64 && C != 128) return cudaErrorNotSupported;
+    if ((reinterpret_cast<uintptr_t>(q) & 15) != 0) return cudaErrorNotSupported;
+    const int kchunks = C / 64;
+    const int mblks = (N + 127) / 128;
+    if (mblks > num_sms) return cudaErrorNotSupported;
+    const int num_tiles = (K + kH1BN - 1) / kH1BN;
+    const int n_pad = mblks * 128;
+    *n_pad_out = n_pad;
+
+    CUtensorMap tm_queue;
+    if (!make_tmap(&tm_queue, queue, K, C, kH1BN)) return cudaErrorUnknown;
+
+    const int tile_bytes = kchunks * kH1Slab;
+    int stages = (kSmemBudget - tile_bytes - 2048) / tile_bytes;     // q tile + 2 KB barriers / exchange array
+    if (stages > 8) stages = 8;
+    if (stages * tile_bytes < 16 * 32 * 33 * 4) return cudaErrorNotSupported;   // the O epilogue stages through the ring
+    const int smem = (stages + 1) * tile_bytes + 2048;
+
+    Head128Args a;
+    a.N = N; a.C = C; a.K = K;
+    a.mblks = mblks; a.slices = 0; a.n_pad = n_pad; a.num_tiles = num_tiles; a.stages = stages;
+    a.inv_T = inv_T;
+    a.q = q; a.q_dtype = q_dtype; a.normalize = normalize;
+    a.lse = lse;
+    a.part_o = ws.part_o;
+    a.part_ms = ws.part_ms;
+    a.counters = ws.counters;
+    auto fill = [](Head128Args& x, int slices) { x.slices = slices; };
+    if (fused)
+        return plan_and_launch(nce_head128_kernel<true>, kernel_cache(0), kH1Threads, smem, 1, mblks, mblks, num_tiles,
+                               n_pad, slices_out, stream, tm_queue, tm_queue, a, fill, true, plan_only);
+    return plan_and_launch(nce_head128_kernel<false>, kernel_cache(1), kH1Threads, smem, 1, mblks, mblks, num_tiles, n_pad,
+                           slices_out, stream, tm_queue, tm_queue, a, fill, true, plan_only);
+}
+
+#ifdef MOCO_TRACE
+extern "C" int moco_debug_h128_trace(long long* host_buf) {
+    return (int)cudaMemcpyFromSymbol(host_buf, g_h128_trace, sizeof(g_h128_trace));
+}
+#endif
+
+}  // namespace moco

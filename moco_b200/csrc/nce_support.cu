@@ -6,58 +6,10 @@
 // Reference semantics: moco/NCE/Contrast.py:20-27, moco/NCE/NCECriterion.py:11-13,
 // train.py:264,273 (see include/moco_b200.h).
 #include "common.cuh"
+#include "nce_rows.cuh"
 #include "sm100_ptx.cuh"
 
 namespace moco {
-
-__device__ __forceinline__ float load_as_float(const void* p, int dtype, size_t idx) {
-    return dtype == 0 ? static_cast<const float*>(p)[idx]
-                      : __bfloat162float(static_cast<const __nv_bfloat16*>(p)[idx]);
-}
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-// Deterministic mean over rows by the last block to finish (fixed summation order).
-__device__ void finish_mean(unsigned int* counter, int N, const float* loss_rows, const float* prob_rows,
-                            float* loss_prob) {
-    __shared__ float s_red[2][32];
-    __shared__ int s_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        unsigned int t = atomicAdd(counter, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    float a = 0.f, b = 0.f;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        a += __ldcg(loss_rows + i);
-        b += __ldcg(prob_rows + i);
-    }
-    a = warp_sum(a);
-    b = warp_sum(b);
-    int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    if ((threadIdx.x & 31) == 0) { s_red[0][w] = a; s_red[1][w] = b; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float sa = 0.f, sb = 0.f;
-        for (int i = 0; i < nw; ++i) { sa += s_red[0][i]; sb += s_red[1][i]; }
-        loss_prob[0] = sa / (float)N;
-        loss_prob[1] = sb / (float)N;
-        *counter = 0u;          // re-arm for the next launch on this workspace
-    }
-}
 
 // ---------------------------------------------------------------------------
 // prep: lpos[i] = <q_i, k_i> (fp32), q_bf16 = bf16(q) when q is fp32, zero counters.
@@ -283,96 +235,27 @@ cudaError_t launch_dq_finish_peers(const void* const* peers_host, int world, int
 // ---------------------------------------------------------------------------
 // Generic CUDA-core path: one block per q row, any (N, C <= 1024, K).
 // ---------------------------------------------------------------------------
-constexpr int kSimtThreads = 256;
-constexpr int kSimtMaxC = 1024;
-
-__device__ __forceinline__ float dot_row(const float* __restrict__ qs, const __nv_bfloat16* __restrict__ row, int C) {
-    float acc = 0.f;
-    if ((C & 7) == 0) {
-        const uint4* r4 = reinterpret_cast<const uint4*>(row);
-        for (int v = 0; v < (C >> 3); ++v) {
-            uint4 u = __ldg(r4 + v);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float2 f = __bfloat1622float2(h[e]);
-                acc = fmaf(qs[v * 8 + e * 2], f.x, acc);
-                acc = fmaf(qs[v * 8 + e * 2 + 1], f.y, acc);
-            }
-        }
-    } else {
-        for (int c = 0; c < C; ++c) acc = fmaf(qs[c], __bfloat162float(row[c]), acc);
-    }
-    return acc;
-}
-
 __global__ void __launch_bounds__(kSimtThreads)
 simt_rows_kernel(const __nv_bfloat16* __restrict__ q_bf16, const void* __restrict__ k, int k_dtype,
                  const __nv_bfloat16* __restrict__ queue, int N, int C, int K, float inv_T,
                  const float* __restrict__ lpos, float* __restrict__ logits, float* __restrict__ lse,
                  float* __restrict__ loss_rows, float* __restrict__ prob_rows, float* __restrict__ loss_prob,
                  float* __restrict__ dq, unsigned int* __restrict__ counters) {
-    __shared__ float qs[kSimtMaxC];
-    __shared__ float ps[kSimtThreads];
-    __shared__ float red_m[kSimtThreads / 32], red_s[kSimtThreads / 32];
-    __shared__ float s_bcast[2];
+    __shared__ SimtRowSmem sm;
     const int i = blockIdx.x, tid = threadIdx.x;
-    const float scale2 = inv_T * kLog2e;
-    for (int c = tid; c < C; c += kSimtThreads) qs[c] = __bfloat162float(q_bf16[(size_t)i * C + c]);
+    for (int c = tid; c < C; c += kSimtThreads) sm.qs[c] = __bfloat162float(q_bf16[(size_t)i * C + c]);
     __syncthreads();
-    const float x0 = lpos[i] * scale2;
-    // pass 1: logits (optional store) + online (max, sum) in the log2 domain
-    float m = -INFINITY, s = 0.f;
-    for (int j = tid; j < K; j += kSimtThreads) {
-        float d = dot_row(qs, queue + (size_t)j * C, C);
-        if (logits) logits[(size_t)i * (K + 1) + 1 + j] = d * inv_T;
-        float x = d * scale2;
-        if (x > m) { s *= ex2(m - x); m = x; }
-        s += ex2(x - m);
-    }
-    // block combine of (m, s)
-    float wm = warp_max(m);
-    float ws_ = warp_sum(m == -INFINITY ? 0.f : s * ex2(m - wm));
-    if ((tid & 31) == 0) { red_m[tid >> 5] = wm; red_s[tid >> 5] = ws_; }
-    __syncthreads();
+    const float lse2 = simt_row_stats(sm, lpos[i], queue, C, K, inv_T, logits ? logits + (size_t)i * (K + 1) : nullptr);
+    const float prob = exp2f(lpos[i] * inv_T * kLog2e - lse2);
     if (tid == 0) {
-        float M = x0;
-        for (int w = 0; w < kSimtThreads / 32; ++w) M = fmaxf(M, red_m[w]);
-        float L = ex2(x0 - M);
-        for (int w = 0; w < kSimtThreads / 32; ++w)
-            if (red_m[w] != -INFINITY) L += red_s[w] * ex2(red_m[w] - M);
-        float lse2 = M + log2f(L);
-        float lse_nat = lse2 * kLn2, x0n = lpos[i] * inv_T, prob = exp2f(x0 - lse2);
+        const float lse_nat = lse2 * kLn2, x0n = lpos[i] * inv_T;
         lse[i] = lse_nat;
         loss_rows[i] = lse_nat - x0n;
         prob_rows[i] = prob;
-        if (logits) logits[(size_t)i * (K + 1)] = x0n;
-        s_bcast[0] = lse2;
-        s_bcast[1] = prob;
     }
-    __syncthreads();
     if (dq) {
-        const float lse2 = s_bcast[0], prob = s_bcast[1];
         float acc[kSimtMaxC / kSimtThreads];
-#pragma unroll
-        for (int u = 0; u < kSimtMaxC / kSimtThreads; ++u) acc[u] = 0.f;
-        for (int jb = 0; jb < K; jb += kSimtThreads) {
-            int j = jb + tid;
-            ps[tid] = (j < K) ? ex2(dot_row(qs, queue + (size_t)j * C, C) * scale2 - lse2) : 0.f;
-            __syncthreads();
-            int jn = min(kSimtThreads, K - jb);
-#pragma unroll
-            for (int u = 0; u < kSimtMaxC / kSimtThreads; ++u) {
-                int c = tid + u * kSimtThreads;
-                if (c < C) {
-                    float a = acc[u];
-                    for (int jj = 0; jj < jn; ++jj)
-                        a = fmaf(ps[jj], __bfloat162float(queue[(size_t)(jb + jj) * C + c]), a);
-                    acc[u] = a;
-                }
-            }
-            __syncthreads();
-        }
+        simt_row_grad(sm, lse2, queue, C, K, inv_T, acc);
         const float gscale = inv_T / (float)N;
 #pragma unroll
         for (int u = 0; u < kSimtMaxC / kSimtThreads; ++u) {

@@ -70,6 +70,9 @@ class MoCoResNet(nn.Module):
                 cin = planes * block.expansion
         self.layers = nn.Sequential(*layers)
         self.fc = nn.Linear(cin, low_dim)
+        # l2norm=False: return the raw fc output -- the contrast head then normalises inside its kernels
+        # (MemoryMoCo.forward_loss(..., normalize=True))
+        self.l2norm = True
         for m in self.modules():
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
@@ -81,6 +84,8 @@ class MoCoResNet(nn.Module):
         x = self.layers(self.stem(x))
         x = torch.flatten(F.adaptive_avg_pool2d(x, 1), 1)
         x = self.fc(x).float()
+        if not self.l2norm:
+            return x
         return x / x.pow(2).sum(1, keepdim=True).sqrt()       # Normalize(power=2), resnet.py:30-33
 
 

@@ -273,6 +273,38 @@ def l2_normalize(x: np.ndarray) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------
+# Normalize layer in front of the head.
+# --------------------------------------------------------------------------
+def normalize_backward(x: np.ndarray, grad_out: np.ndarray) -> np.ndarray:
+    """Gradient through the reference's Normalize layer (moco/models/resnet.py:30-33, out = x / sqrt(sum x^2)):
+    dx = (g - x^ <x^, g>) / |x| with x^ = x / |x| (what autograd produces for pow / sum / pow / div)."""
+    x64, g64 = x.astype(np.float64), grad_out.astype(np.float64)
+    nrm = np.sqrt((x64 * x64).sum(1, keepdims=True))
+    xh = x64 / nrm
+    return ((g64 - xh * (xh * g64).sum(1, keepdims=True)) / nrm)
+
+
+def head_with_normalize(xq: np.ndarray, xk: np.ndarray, memory_pre: np.ndarray, T: float,
+                        round_q_to_bf16: bool = False):
+    """Normalize (resnet.py:24-33) -> MemoryMoCo logits (Contrast.py:20-27) -> NCESoftmaxLoss (NCECriterion.py:11-13)
+    -> prob (train.py:264) -> gradient w.r.t. the RAW xq (train.py:273).  Returns (loss, prob, dxq, q^, k^).
+    round_q_to_bf16 mirrors the kernels' operand contract (include/moco_b200.h): the negatives use bf16(q^), the
+    positive logit the fp32 q^ and k^."""
+    q, k = l2_normalize(xq), l2_normalize(xk)
+    qn = bf16_round(q) if round_q_to_bf16 else q
+    x0 = (q.astype(np.float64) * k.astype(np.float64)).sum(1) / T
+    neg = qn.astype(np.float64) @ memory_pre.astype(np.float64).T / T
+    out = np.concatenate([x0[:, None], neg], 1)
+    lse = logsumexp_rows(out)
+    p = np.exp(out - lse[:, None])
+    loss = float((lse - x0).mean())
+    prob = float(p[:, 0].mean())
+    N = q.shape[0]
+    dq = ((p[:, :1] - 1.0) * k.astype(np.float64) + p[:, 1:] @ memory_pre.astype(np.float64)) / (T * N)
+    return loss, prob, normalize_backward(xq, dq), q, k
+
+
+# --------------------------------------------------------------------------
 # Momentum update of the key encoder.
 # --------------------------------------------------------------------------
 def moment_update(params: Sequence[np.ndarray], params_ema: Sequence[np.ndarray], m: float) -> List[np.ndarray]:

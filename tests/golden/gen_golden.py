@@ -94,6 +94,38 @@ def gen_contrast():
     np.savez_compressed(os.path.join(OUT, "contrast.npz"), **out)
 
 
+# ------------------------------------------------------------------ Normalize -> head
+def gen_normalize():
+    """The reference's own `Normalize` layer (moco/models/resnet.py:24-33) in front of its head, differentiated down
+    to the RAW encoder output: what moco_nce_step(normalize=1) fuses."""
+    from moco.NCE import MemoryMoCo, NCESoftmaxLoss
+    from moco.models.resnet import Normalize
+    out = {}
+    for ci, (name, (N, C, K, A, T)) in enumerate({"n128": (32, 128, 1024, 32, 0.07), "n64": (24, 64, 320, 48, 0.1)}.items()):
+        torch.manual_seed(2000 + ci)
+        contrast = MemoryMoCo(C, K, T)
+        contrast.memory.copy_(bf16r(contrast.memory))
+        l2 = Normalize(2)
+        xq = (torch.randn(N, C) * 3.0).requires_grad_(True)
+        xk = torch.randn(N, C) * 0.5
+        xk_all = torch.randn(A, C) * 2.0
+        xk_all[:min(N, A)] = xk[:min(N, A)]
+        out[f"{name}_meta"] = np.array([N, C, K, A], dtype=np.int64)
+        out[f"{name}_T"] = np.array([T], dtype=np.float64)
+        out[f"{name}_memory0"] = contrast.memory.numpy().copy()
+        q, k, k_all = l2(xq), l2(xk), l2(xk_all)
+        logits = contrast(q, k, k_all)
+        loss = NCESoftmaxLoss()(logits)
+        prob = F.softmax(logits, dim=1)[:, 0].mean()
+        loss.backward()
+        for key, val in dict(xq=xq.detach(), xk=xk, xk_all=xk_all, q=q.detach(), k=k, dxq=xq.grad,
+                             memory_final=contrast.memory).items():
+            out[f"{name}_{key}"] = val.numpy().copy()
+        out[f"{name}_loss"] = np.array([loss.item()], dtype=np.float64)
+        out[f"{name}_prob"] = np.array([prob.item()], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "normalize.npz"), **out)
+
+
 # ------------------------------------------------------------------ ShuffleBN over gloo
 def _shuffle_worker(rank, world, n, epoch, port, ret):
     _shim()
@@ -162,6 +194,7 @@ if __name__ == "__main__":
     gen_ema()
     gen_shuffle_ids()
     gen_contrast()
+    gen_normalize()
     gen_shuffle()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):

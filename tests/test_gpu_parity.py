@@ -174,29 +174,106 @@ def test_low_temperature_both_sweeps(flag):
     lse, loss, prob, dq = oracle_head_chunked(q, k, memory, T)
     before = _lib.launches
     l, p, g = _head_gpu(q, k, memory, T, _flags()[flag])
-    n_launch = _lib.launches - before - 2                # minus f32->bf16 of the queue and the enqueue
-    assert n_launch == (4 if flag == "onepass" else 5), n_launch
+    n_launch = _lib.launches - before - 1                # minus f32->bf16 of the queue
+    # one sweep: the tcgen05 kernel + ONE tail kernel that also enqueues; two-pass: prep, stats, combine, dq,
+    # dq_reduce + the enqueue kernel
+    assert n_launch == (2 if flag == "onepass" else 6), n_launch
     assert abs(l - loss) < 2e-4 * max(1.0, abs(loss)), (l, loss)
     assert abs(p - prob) < 1e-3 * prob + 1e-9
     assert np.abs(g - dq).max() / np.abs(dq).max() < 5e-3
 
 
-def test_one_pass_overflow_is_loud_and_two_pass_is_exact():
+@pytest.mark.parametrize("flag", ["onepass", "twopass"])
+def test_unnormalised_inputs_stay_exact(flag):
     """Un-normalised q (norm 12) with its exact direction queued in the LAST tile of a queue long enough that every
-    CTA sweeps >= 2 tiles: that logit exceeds its CTA's first-tile maximum by > 88 nats, the documented limit of the
-    one-pass kernel -> non-finite loss (never a finite wrong number); the two-pass kernels are exact on the same
-    inputs."""
+    CTA sweeps >= 2 tiles: that logit exceeds its CTA's first-tile maximum by > 127 binades, which the one-sweep
+    kernel cannot represent (its partial sum overflows).  The tail kernel detects such rows and recomputes them
+    exactly on CUDA cores, so the drop-in never diverges from the reference (which returns a finite loss for any q);
+    the two-pass kernels are exact by construction."""
     rng = np.random.default_rng(12)
     N, C, K, T = 64, 128, 2 * 160 * 128, 0.07
     q, k, memory = rand_unit(rng, N, C), rand_unit(rng, N, C), rand_unit(rng, K, C)
     q = O.bf16_round(q * 12.0)
     memory[K - 7] = O.bf16_round(q[3] / 12.0)
     lse, loss, prob, dq = oracle_head_chunked(q, k, memory, T)
-    l2, p2, g2 = _head_gpu(q, k, memory, T, _flags()["twopass"])
-    assert abs(l2 - loss) < 2e-4 * max(1.0, abs(loss)), (l2, loss)
-    assert np.abs(g2 - dq).max() / np.abs(dq).max() < 5e-3
-    l1, _, _ = _head_gpu(q, k, memory, T, _flags()["onepass"])
-    assert not np.isfinite(l1)
+    l, p, g = _head_gpu(q, k, memory, T, _flags()[flag])
+    assert np.isfinite(l) and abs(l - loss) < 2e-4 * max(1.0, abs(loss)), (l, loss)
+    assert abs(p - prob) < 1e-3 * prob + 1e-9
+    assert np.isfinite(g).all() and np.abs(g - dq).max() / np.abs(dq).max() < 5e-3
+
+
+@pytest.mark.parametrize("name", ["n128", "n64"])
+def test_fused_normalize_matches_reference_and_oracle(golden_dir, name):
+    """raw encoder outputs in, L2 normalisation (resnet.py:24-33) inside the head's kernels -- forward for
+    q, k and the enqueued keys, backward for q.  Against the reference's own Normalize + MemoryMoCo + autograd
+    (tests/golden/normalize.npz; bf16 operand quantisation bounds the difference) and tightly against the oracle
+    with the kernels' operand contract."""
+    from moco_b200 import _lib
+    from moco_b200.NCE import MemoryMoCo
+    g = np.load(os.path.join(golden_dir, "normalize.npz"))
+    N, C, K, A = (int(v) for v in g[f"{name}_meta"])
+    T = float(g[f"{name}_T"][0])
+    mod = MemoryMoCo(C, K, T)
+    mod.memory.copy_(torch.from_numpy(g[f"{name}_memory0"]))
+    mod = mod.cuda()
+    xq = torch.from_numpy(g[f"{name}_xq"]).cuda().requires_grad_(True)
+    before = _lib.launches
+    loss, prob = mod.forward_loss(xq, torch.from_numpy(g[f"{name}_xk"]).cuda(), torch.from_numpy(g[f"{name}_xk_all"]).cuda(),
+                                  normalize=True)
+    assert _lib.launches - before == 3                     # f32->bf16 of the fresh queue + sweep + tail: no torch normalise
+    loss.backward()
+    got = xq.grad.cpu().numpy()
+    # vs the reference itself
+    ref = g[f"{name}_dxq"]
+    assert abs(float(loss) - float(g[f"{name}_loss"][0])) < 5e-3
+    assert abs(float(prob) - float(g[f"{name}_prob"][0])) < 5e-3 * float(g[f"{name}_prob"][0]) + 1e-6
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 2e-2
+    # vs the oracle under the kernels' operand contract: tight
+    l2, p2, d2, _, _ = O.head_with_normalize(g[f"{name}_xq"], g[f"{name}_xk"], g[f"{name}_memory0"], T, True)
+    assert abs(float(loss) - l2) < 2e-4 and abs(float(prob) - p2) < 1e-3 * p2
+    assert np.abs(got - d2).max() / np.abs(d2).max() < 5e-3
+    # the enqueued rows are the NORMALISED keys: fp32 master within an ulp of the reference's, ring position advanced
+    np.testing.assert_allclose(mod.memory.cpu().numpy(), g[f"{name}_memory_final"], rtol=0, atol=2e-7)
+    assert mod.index == A % K
+
+
+def test_device_side_ring_index_survives_graph_replay():
+    """SURVEY 8 f2 / Contrast.py:12,32-34: with the ring position in a Python int a captured step would replay the same
+    slots forever; MemoryMoCo(device_index=True) keeps it on the device, advanced by the tail kernel."""
+    from moco_b200.NCE import MemoryMoCo
+    from moco_b200.NCE.Contrast import _nce_forward
+    rng = np.random.default_rng(21)
+    N, C, K, T = 64, 128, 320, 0.07                       # K not a multiple of the batch: wraps on the 5th replay
+    memory = rand_unit(rng, K, C)
+    mods = []
+    for dev_index in (False, True):
+        m = MemoryMoCo(C, K, T, device_index=dev_index)
+        m.memory.copy_(torch.from_numpy(memory))
+        mods.append(m.cuda())
+    eager, graphed = mods
+    sq, sk = torch.zeros(N, C, device="cuda"), torch.zeros(N, C, device="cuda")
+    graphed._queue_bf16(); graphed._index_dev()
+    _nce_forward(graphed, sq, sk, False, True, graphed.kernel_flags, k_all=sk)     # eager warm-up (enqueues zeros)
+    graphed.memory.copy_(torch.from_numpy(memory).cuda()); graphed._invalidate(); graphed._queue_bf16()
+    graphed.index = 0
+    graphed._index_dev()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        _, loss_prob, dq, _, _ = _nce_forward(graphed, sq, sk, False, True, graphed.kernel_flags, k_all=sk)
+    graphed.index = 0
+    graphed._index_shadow = 0
+    for step in range(7):
+        q, k = rand_unit(rng, N, C), rand_unit(rng, N, C)
+        qt = torch.from_numpy(q).cuda().requires_grad_(True)
+        l, p = eager.forward_loss(qt, torch.from_numpy(k).cuda(), torch.from_numpy(k).cuda())
+        l.backward()
+        sq.copy_(torch.from_numpy(q)); sk.copy_(torch.from_numpy(k))
+        g.replay()
+        assert float(loss_prob[0]) == float(l) and float(loss_prob[1]) == float(p), step
+        assert torch.equal(dq.to(qt.grad.dtype), qt.grad), step
+    torch.cuda.synchronize()
+    assert torch.equal(graphed.memory, eager.memory)
+    assert graphed.sync_index() == eager.index == (7 * N) % K
 
 
 def test_fp32_inputs_are_rounded_to_bf16_exactly_once():
@@ -648,3 +725,42 @@ def test_step_with_fused_input_path_matches_plain_step():
     for (l0, p0), (l1, p1) in zip(*losses):
         assert abs(l0 - l1) < 1e-2 * max(1.0, abs(l0)), (losses)
         assert abs(p0 - p1) < 5e-2 * max(p0, 1e-6) + 1e-6
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_step_with_fused_normalize_and_graphed_tail_matches_plain_step(graph):
+    """MoCoStep(fuse_normalize=True[, graph_tail=True]) takes the encoders' RAW fc outputs, normalises
+    inside the head's two kernels (forward for q / k / the enqueued keys, backward for q) and -- graph_tail -- replays
+    the whole post-encoder tail from one captured CUDA graph with the ring position on the device.  Same math as the
+    plain step (Normalize in torch, eager tail): same losses, same queue, same ring position."""
+    from moco_b200 import encoders
+    from moco_b200.NCE import MemoryMoCo
+    from moco_b200.train_step import MoCoStep
+    runs = []
+    for fused in (False, True):
+        torch.manual_seed(0)
+        model = encoders.resnet18(low_dim=128).cuda()
+        ema = encoders.resnet18(low_dim=128).cuda()
+        ema.load_state_dict(model.state_dict())
+        contrast = MemoryMoCo(128, 80, 0.07, device_index=fused and graph).cuda()      # K = 80, 16 keys/step: wraps
+        opt = torch.optim.SGD(model.parameters(), lr=0.03, momentum=0.9, weight_decay=1e-4)
+        step = MoCoStep(model, ema, contrast, opt, amp_dtype=None, fuse_normalize=fused, graph_tail=fused and graph)
+        g = torch.Generator(device="cuda").manual_seed(4)
+        out = []
+        for _ in range(7):
+            batch = torch.randn(16, 6, 64, 64, device="cuda", generator=g)
+            x1, x2 = torch.split(batch, [3, 3], dim=1)
+            loss, prob = step(x1.contiguous(), x2.contiguous(), 1)
+            out.append((float(loss), float(prob)))
+        torch.cuda.synchronize()
+        runs.append((out, contrast.memory.cpu().numpy().copy(), contrast.sync_index() if fused and graph else contrast.index,
+                     next(model.parameters()).detach().cpu().numpy().copy()))
+    (o0, m0, i0, w0), (o1, m1, i1, w1) = runs
+    assert i0 == i1 == (7 * 16) % 80
+    for (l0, p0), (l1, p1) in zip(o0, o1):
+        assert abs(l0 - l1) < 1e-2 * max(1.0, abs(l0)), (o0, o1)
+        assert abs(p0 - p1) < 5e-2 * max(p0, 1e-6) + 1e-6
+    # the queue holds normalised keys in the same slots; the trained weights followed the same trajectory
+    np.testing.assert_allclose(m0, m1, atol=5e-3)
+    np.testing.assert_allclose(np.linalg.norm(m1, axis=1), 1.0, atol=1e-3)
+    np.testing.assert_allclose(w0, w1, atol=5e-3)

@@ -147,3 +147,26 @@ def test_one_sweep_overflow_contract():
     assert np.abs(lse1 - O.logsumexp_rows(out1)).max() < 2e-5 * np.abs(out1).max()
     ref_dq = O.nce_backward_dq(q / 12.0, k, mem, T)
     assert np.abs(dq1 - ref_dq).max() / np.abs(ref_dq).max() < 1e-4
+
+
+def test_normalize_head_matches_reference(golden_dir):
+    """Normalize (resnet.py:24-33) -> head -> gradient w.r.t. the RAW encoder output, against the reference's own
+    autograd (tests/golden/normalize.npz)."""
+    g = np.load(os.path.join(golden_dir, "normalize.npz"))
+    for name in ("n128", "n64"):
+        N, C, K, A = (int(v) for v in g[f"{name}_meta"])
+        T = float(g[f"{name}_T"][0])
+        loss, prob, dxq, q, k = O.head_with_normalize(g[f"{name}_xq"], g[f"{name}_xk"], g[f"{name}_memory0"], T)
+        np.testing.assert_allclose(q, g[f"{name}_q"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(k, g[f"{name}_k"], rtol=0, atol=1e-6)
+        assert abs(loss - float(g[f"{name}_loss"][0])) < 1e-5
+        assert abs(prob - float(g[f"{name}_prob"][0])) < 1e-6
+        ref = g[f"{name}_dxq"]
+        assert np.abs(dxq - ref).max() / np.abs(ref).max() < 1e-4
+        # enqueue of the normalised keys (Contrast.py:29-34)
+        orc = O.MemoryMoCoOracle(g[f"{name}_memory0"], T)
+        orc.enqueue(O.l2_normalize(g[f"{name}_xk_all"]))
+        np.testing.assert_allclose(orc.memory, g[f"{name}_memory_final"], rtol=0, atol=1e-6)
+        # the kernels' operand contract (bf16 q^ for the negatives) stays within the bf16 quantisation of the logits
+        l2, p2, d2, _, _ = O.head_with_normalize(g[f"{name}_xq"], g[f"{name}_xk"], g[f"{name}_memory0"], T, True)
+        assert abs(l2 - loss) < 5e-3 and np.abs(d2 - dxq).max() / np.abs(dxq).max() < 2e-2

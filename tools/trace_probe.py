@@ -45,12 +45,14 @@ def main():
         assert rc == 0, lib.moco_last_error()
     torch.cuda.synchronize()
     buf = (ctypes.c_longlong * (4 * 64 * 8))()
-    assert raw.moco_debug_dq2_trace(buf) == 0
+    # C <= 128 runs on nce_head128_sm100.cu, C in {192, 256} on nce_dq2_sm100.cu: each has its own trace buffer
+    assert (raw.moco_debug_h128_trace if C <= 128 else raw.moco_debug_dq2_trace)(buf) == 0
     t = [[[buf[(r * 64 + i) * 8 + s] for s in range(8)] for i in range(64)] for r in range(4)]
     base = min(v for r in t for row in r for v in row if v > 0)
     names = {0: "MMA : waitP  gotP  PVissued commitKV | waitKV gotKV Sissued commitS",
              1: "SM g0: waitS gotS ld0done st0 allst stwait arrived", 2: "SM g1: (same)",
-             3: "KERNEL: entry setup_done q_staged o_full O_written all_done"}
+             3: ("KERNEL (C<=128): entry pdl_wait_done setup_done q_data q_staged o_full O_written all_done | row 1: S-issuer got q"
+                 if C <= 128 else "KERNEL: entry setup_done q_staged o_full O_written all_done")}
     for r in range(4):
         print(names[r])
         for i in range(min(64, 24)):
