@@ -23,14 +23,15 @@
 // tensor work.  Warp 1 issues S, warp 3 issues P.V; S(i+3) overwriting the buffer P.V(i) reads P from is ordered by
 // the s_free mbarrier P.V(i)'s tcgen05.commit arrives on.
 //
-// Stabiliser (FUSED = true, no lse yet): m_i = (log2e / T) * |q_i|, computed from the row while it is staged -- an
-// upper bound of every logit of the row against unit-norm queue rows, so no pass over the first S tile is needed to
-// find a maximum (that pre-pass cost every CTA ~700 cycles of its critical path).  P~ = 2^(x - m), l = sum P~,
-// O~ = sum P~ queue_j; the tail kernel (nce_tail.cu) merges the per-slice (m, l) pairs and rescales each slice's O~
-// by 2^(m - lse).  All terms of a row share the exponent offset, so precision is that of the exponent-free bf16 / fp32
-// formats; what can go wrong is only the exponent RANGE (queue rows far above unit norm: overflow; logits far below
-// the bound, e.g. un-normalised q: everything flushes to zero).  The tail kernel detects both (l > 2^100 or the total
-// < 2^-80) and recomputes such rows exactly, so the result is never silently wrong.
+// Stabiliser (FUSED = true, no lse yet): the CONSTANT m = log2e / T -- the largest logit a unit-norm query can have
+// against a unit-norm queue row -- so neither a pass over the first S tile (it cost every CTA ~700 cycles of its
+// critical path) nor a row norm (40 dependent shuffles per warp in front of the first MMA) is needed.  P~ = 2^(x - m),
+// l = sum P~, O~ = sum P~ queue_j; the tail kernel (nce_tail.cu) merges the per-slice (m, l) pairs and rescales each
+// slice's O~ by 2^(m - lse).  All terms of a row share the exponent offset, so precision is that of the exponent-free
+// bf16 / fp32 formats; what can go wrong is only the exponent RANGE: rows far from unit norm (the reference's
+// U(-s, s) initial queue rows, norm <= sqrt(3), are fine: P~ <= 2^16).  The tail kernel detects both directions
+// (a slice sum > 2^100, or a merged sum < 2^-80) and recomputes such rows exactly on CUDA cores, so the result is
+// never silently wrong and equals the reference's for ANY q.
 // FUSED = false: P is normalised with the given lse (two-pass mode, after the statistics kernel).
 //
 // Replaces torch.mm + cat + div + CrossEntropyLoss + softmax and autograd's backward GEMM with its queue clone
@@ -93,7 +94,6 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
     uint64_t* s_free = bars + 2 * NS + 8;                  // [3]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 11);
     float* exch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);     // [3][128] floats
-    float* mrow = exch + 2 * kRowsPerCta;      // [128] row stabilisers: read once at the start; the slot is reused for the final sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mblk = blockIdx.x % a.mblks;
@@ -122,21 +122,25 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
     // q rows of this block: 16 warps x 8 rows, one coalesced row load per (warp, row), all 8 in flight before the
     // set-up barrier (their latency is the kernel's critical path at small K)
     if (threadIdx.x == 0) MOCO_TR(3, 0, 1);
-    // RAW bits only: nothing may consume a loaded value before the barrier below, or the load latency lands in front of it
+    // Each softmax warp owns 8 consecutive q rows = 8 * C * esz contiguous bytes, fetched as 16-byte-per-lane loads
+    // (512 B per instruction: 2, 4 or 8 instructions).  RAW bits only: nothing may consume a loaded value before the
+    // barrier below, or the load latency lands in front of it.
     uint4 qraw[8];
-    const int epl = a.C >> 5;                              // elements per lane: 2 (C = 64) or 4 (C = 128)
-    const int qbytes = epl * (a.q_dtype == MOCO_F32 ? 4 : 2);   // bytes per lane per row: 4, 8 or 16
+    const int esz = (a.q_dtype == MOCO_F32) ? 4 : 2;
+    const int row_bytes = a.C * esz;                       // 128, 256 or 512
+    const int rb_shift = 31 - __clz(row_bytes);            // a power of two: shifts, not divisions, in front of the loads
+    const int n_ld = row_bytes >> 6;                       // 8 rows * row_bytes / 512
     if (warp >= 4) {
         const int sw = warp - 4;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int grow = row0 + sw * 8 + j;
-            const int srow = grow < a.N ? grow : 0;        // clamped: padding rows are zeroed when they are staged
-            const uint8_t* src = static_cast<const uint8_t*>(a.q) + ((size_t)srow * a.C + lane * epl) * (a.q_dtype == MOCO_F32 ? 4 : 2);
-            qraw[j] = make_uint4(0u, 0u, 0u, 0u);
-            if (qbytes == 16)     qraw[j] = __ldg(reinterpret_cast<const uint4*>(src));
-            else if (qbytes == 8) { const uint2 u = __ldg(reinterpret_cast<const uint2*>(src)); qraw[j].x = u.x; qraw[j].y = u.y; }
-            else                  qraw[j].x = __ldg(reinterpret_cast<const uint32_t*>(src));
+        for (int t = 0; t < 8; ++t) {
+            qraw[t] = make_uint4(0u, 0u, 0u, 0u);
+            if (t < n_ld) {
+                const int o = t * 512 + lane * 16;         // byte offset inside the warp's 8-row block
+                const int grow = row0 + sw * 8 + (o >> rb_shift);
+                const uint8_t* src = static_cast<const uint8_t*>(a.q) + ((size_t)(grow < a.N ? grow : 0) << rb_shift) + (o & (row_bytes - 1));
+                qraw[t] = __ldg(reinterpret_cast<const uint4*>(src));
+            }
         }
     }
     tc_fence_before();
@@ -235,48 +239,57 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
         const float scale2 = a.inv_T * kLog2e;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
         {
-            // q rows sw*8 .. sw*8+7 -> shared memory, K-major 128B-swizzle (row r at r*128 B inside a 64-column slab,
-            // 16-byte chunk c at position c ^ (r & 7)): exactly what a TMA load of the bf16 tensor would have written
+            // -> shared memory, K-major 128B-swizzle (row r at r*128 B inside a 64-column slab, 16-byte chunk c at
+            // position c ^ (r & 7)): exactly what a TMA load of the bf16 tensor would have written
+            const int lanes_per_row = row_bytes >> 4;      // 8, 16 or 32 lanes hold one row
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int r = sw * 8 + j;
-                float v0, v1, v2 = 0.f, v3 = 0.f;
-                if (a.q_dtype == MOCO_F32) {
-                    v0 = __uint_as_float(qraw[j].x); v1 = __uint_as_float(qraw[j].y);
-                    if (epl == 4) { v2 = __uint_as_float(qraw[j].z); v3 = __uint_as_float(qraw[j].w); }
-                } else {
-                    const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qraw[j].x));
-                    v0 = lo.x; v1 = lo.y;
-                    if (epl == 4) {
-                        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qraw[j].y));
-                        v2 = hi.x; v3 = hi.y;
+            for (int t = 0; t < 8; ++t) {
+                if (t < n_ld) {
+                    const int o = t * 512 + lane * 16;
+                    const int r = sw * 8 + (o >> rb_shift);                    // row inside the CTA's 128-row block
+                    const int col0 = (o & (row_bytes - 1)) >> (esz == 4 ? 2 : 1);
+                    const bool pad = row0 + r >= a.N;
+                    if (t == 0 && sw == 0 && lane == 0) MOCO_TR(3, 0, 3);     // first q data in registers
+                    if (a.q_dtype == MOCO_F32) {           // 4 fp32 -> 4 bf16 (8 bytes)
+                        float v0 = __uint_as_float(qraw[t].x), v1 = __uint_as_float(qraw[t].y);
+                        float v2 = __uint_as_float(qraw[t].z), v3 = __uint_as_float(qraw[t].w);
+                        if (a.normalize) {                 // x / sqrt(sum x^2): resnet.py:31-32
+                            float ss = v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3;
+                            for (int w = lanes_per_row >> 1; w > 0; w >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, w);
+                            const float n = sqrtf(ss);
+                            v0 = v0 / n; v1 = v1 / n; v2 = v2 / n; v3 = v3 / n;
+                        }
+                        if (pad) { v0 = v1 = v2 = v3 = 0.f; }                 // (0/0 of a padding row must not reach the MMA)
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1), hi = __floats2bfloat162_rn(v2, v3);
+                        uint8_t* dst = q_s + (col0 >> 6) * kH1Slab + r * 128 + ((((col0 & 63) >> 3) ^ (r & 7)) << 4) + (col0 & 7) * 2;
+                        *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo),
+                                                                    *reinterpret_cast<const uint32_t*>(&hi));
+                    } else {                               // 8 bf16 = one 16-byte swizzle chunk
+                        uint4 u = qraw[t];
+                        if (a.normalize) {
+                            float f[8];
+                            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+                            float ss = 0.f;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 x = __bfloat1622float2(h[e]);
+                                f[2 * e] = x.x; f[2 * e + 1] = x.y;
+                                ss = fmaf(x.x, x.x, fmaf(x.y, x.y, ss));
+                            }
+                            for (int w = lanes_per_row >> 1; w > 0; w >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, w);
+                            const float n = sqrtf(ss);
+                            __nv_bfloat162 o2[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e] / n, f[2 * e + 1] / n);
+                            u = *reinterpret_cast<const uint4*>(o2);
+                        }
+                        if (pad) u = make_uint4(0u, 0u, 0u, 0u);
+                        uint8_t* dst = q_s + (col0 >> 6) * kH1Slab + r * 128 + ((((col0 & 63) >> 3) ^ (r & 7)) << 4);
+                        *reinterpret_cast<uint4*>(dst) = u;
                     }
                 }
-                if (j == 0 && sw == 0 && lane == 0) MOCO_TR(3, 0, 3);     // first q data in registers
-                if (row0 + r >= a.N) { v0 = v1 = v2 = v3 = 0.f; }
-                float ss = v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                float nrm = sqrtf(ss);
-                if (a.normalize) {
-                    v0 = v0 / nrm; v1 = v1 / nrm; v2 = v2 / nrm; v3 = v3 / nrm;      // x / sqrt(sum x^2): resnet.py:31-32
-                    if (row0 + r >= a.N) { v0 = v1 = v2 = v3 = 0.f; }                // padding rows: 0/0 must not reach the MMA
-                    nrm = 1.f;
-                }
-                if (lane == 0) mrow[r] = nrm * a.inv_T * kLog2e;                     // the row's stabiliser (one-sweep mode)
-                const __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1);
-                if (epl == 4) {
-                    const __nv_bfloat162 hi = __floats2bfloat162_rn(v2, v3);
-                    const int col = lane * 4;
-                    uint8_t* dst = q_s + (col >> 6) * kH1Slab + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) + (col & 7) * 2;
-                    *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo),
-                                                                *reinterpret_cast<const uint32_t*>(&hi));
-                } else {
-                    const int col = lane * 2;
-                    uint8_t* dst = q_s + r * 128 + (((col >> 3) ^ (r & 7)) << 4) + (col & 7) * 2;
-                    *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(&lo);
-                }
             }
+            if (sw == 0 && lane == 0) MOCO_TR(3, 2, 1);                   // smem stores issued
             fence_proxy_async();                          // generic-proxy smem writes -> visible to tcgen05.mma
             __syncwarp();
             if (lane == 0) mbar_arrive(q_ready);
@@ -286,10 +299,7 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
         const bool ragged = (a.K % kH1BN) != 0;
         float lse2 = (!FUSED && grow < a.N) ? a.lse[grow] * kLog2e : 0.f;
         float lsum = 0.f;
-        if (FUSED) {
-            named_bar_sync(1, 16 * 32);                   // every softmax warp has staged its rows: mrow[] is complete
-            lse2 = mrow[row_local];
-        }
+        if (FUSED) lse2 = scale2;                         // the stabiliser of unit-norm rows (see the header comment)
         const bool tracer = (quarter == 0 && chalf == 0 && lane == 0);
         uint32_t b = (uint32_t)grp;                       // buffer of tile i = i % 3, advanced by 2 per iteration
         uint32_t use = 0;                                 // i / 3
@@ -338,7 +348,6 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
         }
         if (FUSED) {
             const int part = grp * 2 + chalf;
-            named_bar_sync(1, 16 * 32);                   // every thread has long read mrow[]: its slot becomes exch[2]
             if (part > 0) exch[(part - 1) * kRowsPerCta + row_local] = lsum;
             named_bar_sync(2 + quarter, 128);
             if (part == 0)
@@ -365,7 +374,7 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
                 for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
                 __syncwarp();
 #pragma unroll
-                for (int k2 = 0; k2 < 32; ++k2) oblk[(size_t)k2 * a.C + c] = tbuf[k2 * 33 + lane];
+                for (int k2 = 0; k2 < 32; ++k2) __stcs(oblk + (size_t)k2 * a.C + c, tbuf[k2 * 33 + lane]);
                 __syncwarp();
             }
         }

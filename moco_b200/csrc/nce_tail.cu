@@ -12,8 +12,12 @@
 //   last block           mean loss / mean prob in fixed order (no float atomics).
 //
 // The head kernel has finished before any block passes pdl_wait(), so the enqueue cannot disturb the logits of this
-// step (the reference reads a clone for the same reason, Contrast.py:24-25).  This kernel WRITES the queue, so it never
-// triggers its dependents early: the next kernel that reads the queue starts after it has completed.
+// step (the reference reads a clone for the same reason, Contrast.py:24-25).  The exact fallback below DOES read the
+// queue inside this kernel, so the enqueue blocks load and convert their key rows first and then hold their stores
+// until every row block has signalled that it is done with the queue (counters[1]; row blocks have the lower block
+// indices and are dispatched first, so the wait cannot starve them; it is bounded and traps rather than hangs).
+// This kernel WRITES the queue, so it never triggers its dependents early: the next kernel that reads the queue
+// starts after it has completed.
 //
 // Exactness: the head kernels work with a per-row exponent offset m (C <= 128: the bound log2e/T |q_i|; C > 128: the
 // row maximum of the CTA's first tile).  If a slice's partial sum left the safe range (> 2^100: logits far above m) or
@@ -221,11 +225,16 @@ nce_tail_kernel(const TailArgs a) {
             a.loss_rows[i] = lse_nat - lpos * a.inv_T;
             a.prob_rows[i] = prob;
         }
+        if (a.n_all > 0) {                                // this block no longer reads the queue: release the enqueue
+            __syncthreads();
+            if (tid == 0) { __threadfence(); atomicAdd(a.counters + 1, 1u); }
+        }
     } else if (a.n_all > 0) {
         // ---- enqueue blocks: queue[(ring + r) mod K] = k_all[r] (fp32 master + bf16 working copy), 8 elements per thread
         const int vec_per_row = a.C >> 3;
         const int rows_per_pass = kTailThreads / vec_per_row;
         const int v = tid % vec_per_row, rl = tid / vec_per_row;
+        bool released = false;
         for (int r0 = ((int)blockIdx.x - a.N) * rows_per_pass; r0 < a.n_all; r0 += a.enq_blocks * rows_per_pass) {
             const int r = r0 + rl;
             const bool live = rl < rows_per_pass && r < a.n_all;
@@ -251,6 +260,17 @@ nce_tail_kernel(const TailArgs a) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = f[e] / nrm;
             }
+            if (!released) {                              // the first pass's rows are loaded and converted: now wait
+                if (tid == 0) {
+                    unsigned int seen, spins = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.counters + 1) : "memory");
+                        if (++spins > (1u << 26)) __trap();
+                    } while (seen < (unsigned int)a.N);
+                }
+                __syncthreads();
+                released = true;
+            }
             if (live) {
                 const long long dst = (ring + r) % a.K - a.row0;          // ring slot, relative to the rows this buffer holds
                 if (dst >= 0 && dst < a.nrows) {
@@ -269,7 +289,10 @@ nce_tail_kernel(const TailArgs a) {
         }
     }
     const bool last = finish_mean(a.counters + 0, a.N, a.loss_rows, a.prob_rows, a.loss_prob);
-    if (last && tid == 0 && a.index_dev != nullptr && a.n_all > 0) *a.index_dev = (ring + a.n_all) % a.K;
+    if (last && tid == 0) {
+        a.counters[1] = 0u;                               // re-arm (every enqueue block has passed its wait: it arrived here)
+        if (a.index_dev != nullptr && a.n_all > 0) *a.index_dev = (ring + a.n_all) % a.K;
+    }
 }
 
 // can the tail kernel also do the enqueue for this shape?

@@ -51,7 +51,7 @@ def main():
     base = min(v for r in t for row in r for v in row if v > 0)
     names = {0: "MMA : waitP  gotP  PVissued commitKV | waitKV gotKV Sissued commitS",
              1: "SM g0: waitS gotS ld0done st0 allst stwait arrived", 2: "SM g1: (same)",
-             3: ("KERNEL (C<=128): entry pdl_wait_done setup_done q_data q_staged o_full O_written all_done | row 1: S-issuer got q"
+             3: ("KERNEL (C<=128): entry pdl_wait_done setup_done q_data q_staged o_full O_written all_done | row 1: S-issuer got q | row 2: rows converted, smem stores issued, fence.proxy.async done"
                  if C <= 128 else "KERNEL: entry setup_done q_staged o_full O_written all_done")}
     for r in range(4):
         print(names[r])
