@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmoco_b200.so")
-SOURCES = ["capi.cu", "nce_support.cu", "nce_tail.cu", "nce_sm100.cu", "nce_head128_sm100.cu", "nce_dq2_sm100.cu",
+SOURCES = ["capi.cu", "nce_support.cu", "nce_tail.cu", "nce_sm100.cu", "nce_head128_sm100.cu", "nce_head256_sm100.cu",
            "queue_shuffle.cu", "ema.cu"]
 HEADERS = ["common.cuh", "sm100_ptx.cuh", "tc_common.cuh", "nce_rows.cuh", os.path.join("..", "..", "include", "moco_b200.h")]
 NVCC_FLAGS = [

@@ -107,7 +107,10 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
     // ---- set-up that touches no global memory (overlaps the predecessor kernel under PDL) ----
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_queue);
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        // kv_full[s] completes on TWO arrivals: the TMA fill of the tile (expect_tx) AND the tcgen05.commit of the P.V
+        // MMA that last read the S/P buffer the tile's S will overwrite -- one wait per tile for the S-issuer instead of
+        // two (an mbarrier wait costs its thread ~100-200 cycles even when the phase has long completed)
+        for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 2); mbar_init(&kv_empty[s], 1); }
         for (int b = 0; b < kH1Bufs; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); mbar_init(&s_free[b], 1); }
         mbar_init(o_full, 1);
         mbar_init(q_ready, 16);
@@ -130,14 +133,16 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
     const int row_bytes = a.C * esz;                       // 128, 256 or 512
     const int rb_shift = 31 - __clz(row_bytes);            // a power of two: shifts, not divisions, in front of the loads
     const int n_ld = row_bytes >> 6;                       // 8 rows * row_bytes / 512
+    // All CTAs of an m-block read the same 128 q rows at the same moment: each starts at a different 8-row block
+    // (rotation by the slice index) so that the requests spread over the L2 slices instead of queueing on a few lines.
+    const int qblk = (warp - 4 + slice) & 15;              // the 8-row block this softmax warp stages
     if (warp >= 4) {
-        const int sw = warp - 4;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             qraw[t] = make_uint4(0u, 0u, 0u, 0u);
             if (t < n_ld) {
                 const int o = t * 512 + lane * 16;         // byte offset inside the warp's 8-row block
-                const int grow = row0 + sw * 8 + (o >> rb_shift);
+                const int grow = row0 + qblk * 8 + (o >> rb_shift);
                 const uint8_t* src = static_cast<const uint8_t*>(a.q) + ((size_t)(grow < a.N ? grow : 0) << rb_shift) + (o & (row_bytes - 1));
                 qraw[t] = __ldg(reinterpret_cast<const uint4*>(src));
             }
@@ -150,12 +155,13 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
     if (threadIdx.x == 0) MOCO_TR(3, 0, 2);
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ------------------------------------------------ TMA producer (queue tiles)
             int st = 0;
             uint32_t ph = 0;
             for (int i = 0; i < ntiles; ++i, st = (st + 1 == NS) ? 0 : st + 1, ph ^= (st == 0) ? 1u : 0u) {
                 mbar_wait(&kv_empty[st], ph ^ 1u);
+                if (i < kH1Bufs) mbar_arrive(&kv_full[st]);             // no earlier P.V to wait for
                 mbar_arrive_expect_tx(&kv_full[st], (uint32_t)tile_bytes);
                 for (int kc = 0; kc < kchunks; ++kc)
                     tma_load_2d(&tm_queue, &kv_full[st], v_s + (size_t)st * tile_bytes + kc * kH1Slab, kc * 64,
@@ -163,7 +169,7 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ------------------------------------------------ MMA issuer 1 of 2: S = q . tile^T (both operands in smem)
             const uint32_t idesc_s = make_idesc_bf16(128, kH1BN, 0, 0);
             mbar_wait(q_ready, 0);
@@ -176,8 +182,7 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
             int s_st = 0; uint32_t s_ph = 0; uint64_t s_vdesc = vk_desc0; uint32_t s_b = 0, s_use = 0;
             for (int i = 0; i < ntiles; ++i) {
                 MOCO_TR(0, i, 4);
-                mbar_wait(&kv_full[s_st], s_ph);
-                if (s_use > 0) mbar_wait(&s_free[s_b], (s_use - 1u) & 1u);      // P.V(i-3) has consumed P in buffer s_b
+                mbar_wait(&kv_full[s_st], s_ph);          // tile landed AND P.V(i-3) has consumed P in buffer s_b
                 tc_fence_after();
                 MOCO_TR(0, i, 5);
                 const uint32_t d = tmem_base + kH1SCol + s_b * (uint32_t)kH1BN;
@@ -199,16 +204,17 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
             }
         }
     } else if (warp == 3) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ------------------------------------------------ MMA issuer 2 of 2: O += P . tile (P in TMEM, tile MN-major)
             const uint32_t idesc_o = make_idesc_bf16(128, (uint32_t)a.C, 0, 1);
             const uint64_t vm_desc0 = make_sw128_desc(smem_u32(v_s), kH1Slab, 1024);
             const uint64_t tile_units = (uint64_t)(tile_bytes >> 4);
-            int o_st = 0; uint32_t o_kph = 0; uint64_t o_vdesc = vm_desc0; uint32_t o_b = 0, o_ph = 0;
+            int o_st = 0; uint64_t o_vdesc = vm_desc0; uint32_t o_b = 0, o_ph = 0;
             for (int i = 0; i < ntiles; ++i) {
                 MOCO_TR(0, i, 0);
+                // p_full alone orders this thread after the tile's TMA fill: softmax(i) arrived here after it saw
+                // s_full, which S(i)'s commit raised after the S-issuer had observed kv_full
                 mbar_wait(&p_full[o_b], o_ph);
-                mbar_wait(&kv_full[o_st], o_kph);         // complete long ago (S(i) read the tile); observed for visibility
                 tc_fence_after();
                 MOCO_TR(0, i, 1);
 #pragma unroll
@@ -220,10 +226,14 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
                 }
                 MOCO_TR(0, i, 2);
                 umma_commit<1>(&kv_empty[o_st]);
-                if (i + kH1Bufs < ntiles) umma_commit<1>(&s_free[o_b]);
+                if (i + kH1Bufs < ntiles) {               // second arrival on the barrier S(i+3) waits on (its tile's stage)
+                    int st3 = o_st + kH1Bufs;
+                    if (st3 >= NS) st3 -= NS;
+                    umma_commit<1>(&kv_full[st3]);
+                }
                 MOCO_TR(0, i, 3);
                 o_vdesc += tile_units;
-                if (++o_st == NS) { o_st = 0; o_kph ^= 1u; o_vdesc = vm_desc0; }
+                if (++o_st == NS) { o_st = 0; o_vdesc = vm_desc0; }
                 if (++o_b == kH1Bufs) { o_b = 0; o_ph ^= 1u; }
             }
             umma_commit<1>(o_full);
@@ -246,7 +256,7 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
             for (int t = 0; t < 8; ++t) {
                 if (t < n_ld) {
                     const int o = t * 512 + lane * 16;
-                    const int r = sw * 8 + (o >> rb_shift);                    // row inside the CTA's 128-row block
+                    const int r = qblk * 8 + (o >> rb_shift);                  // row inside the CTA's 128-row block
                     const int col0 = (o & (row_bytes - 1)) >> (esz == 4 ? 2 : 1);
                     const bool pad = row0 + r >= a.N;
                     if (t == 0 && sw == 0 && lane == 0) MOCO_TR(3, 0, 3);     // first q data in registers

@@ -108,7 +108,7 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ------------------------------------------------ TMA producer
             // NOTE (measured, tools/trace_probe.py): the producer and the MMA issuer are single threads whose
             // scalar instruction stream runs at ~4-6 cycles per dependent instruction; a runtime `it % NS`,
@@ -142,7 +142,10 @@ nce_stats_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        // elect.sync (not `lane == 0`): ptxas then knows a single thread runs the region and issues the tcgen05.mma
+        // instructions back to back from uniform registers; under a threadIdx predicate it wraps EVERY MMA in an
+        // elect/branch loop (~65-90 cycles per MMA, the "issue-bound" limit of round 1)
+        if (rank == 0 && elect_one()) {
             // ------------------------------------------------ MMA issuer (pair leader only)
             const uint32_t idesc = make_idesc_bf16(128 * G, kStatsBN, 0, 0);
             // descriptors differ from tile to tile only in the 14-bit start-address field: build once, then add

@@ -33,6 +33,7 @@
 namespace moco {
 
 constexpr int kTailThreads = kSimtThreads;         // 256
+constexpr int kMaxTailDevices = 64;
 constexpr int kTailMaxSlices = kMaxCtas;           // 160
 constexpr float kTailUnsafeSum = 1.2676506e30f;    // 2^100
 constexpr float kTailUnderflow = 8.2718061e-25f;   // 2^-80
@@ -327,6 +328,13 @@ cudaError_t launch_nce_tail(int N, int C, int K, int slices, int n_pad, float in
         const int rows_per_pass = kTailThreads / vec_per_row;
         a.enq_blocks = (n_all + rows_per_pass - 1) / rows_per_pass;
         if (a.enq_blocks > 148) a.enq_blocks = 148;
+    }
+    // same shared-memory carve-out as the 227 KB head kernel in front of it: no SM reconfiguration between the two
+    static bool carveout_set[kMaxTailDevices] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxTailDevices && !carveout_set[dev]) {
+        cudaFuncSetAttribute(nce_tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carveout_set[dev] = true;
     }
     return launch_pdl(nce_tail_kernel, dim3(N + a.enq_blocks), dim3(kTailThreads), 0, stream, a);
 }
