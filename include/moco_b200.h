@@ -246,6 +246,12 @@ int moco_ema_update(const void* segs_dev, const int32_t* chunk_prefix_dev, int n
 int moco_crop_to_nhwc_bf16(const void* src, int src_dtype, long long src_image_stride, void* dst_bf16,
                            int N, int C, int HW, void* stream);
 
+/* The same with a row permutation: dst image i = crop of src image src_rows[i] (device int64 [N]; NULL = identity).
+ * On ONE GPU this is the whole ShuffleBN forward permute (moco/util.py:69-79) fused with the input path: the
+ * permutation is the address computation of the one pass over the images. */
+int moco_crop_gather_nhwc_bf16(const void* src, int src_dtype, long long src_image_stride, const int64_t* src_rows,
+                               void* dst_bf16, int N, int C, int HW, void* stream);
+
 /* ------------------------------------------------------------------------
  * ShuffleBN row gather over NVLink peer memory.  Replaces dist_collect +
  * fancy-index (moco/util.py:47-58,74-79,88-91): instead of all_gather-ing every
@@ -268,12 +274,26 @@ int moco_shuffle_gather(const void* const* peer_base_host, int world, int rows_p
                         const int64_t* src_rows, int n_rows, size_t row_bytes,
                         void* dst, int flags, void* stream);
 
+/* The same gather with the cross-GPU synchronisation folded into the SAME kernel (ShuffleBN forward = publish + this
+ * one launch): block 0 publishes "rank `rank` has finished writing its staging buffer" (event number `epoch`) into
+ * every peer's signal pad, and every block waits until all `world` peers have published that event before its first
+ * pull.  Pads and epoch numbering are those of moco_signal_barrier (one event = one epoch, whichever call carries it).
+ * The wait is bounded in time (MOCO_BARRIER_TIMEOUT_MS, default 120000): on expiry the kernel records the reason in a
+ * pinned status block (moco_p2p_last_timeout) and traps. */
+int moco_shuffle_gather_sync(const void* const* peer_base_host, void* const* signal_pads_host, int world, int rank,
+                             uint32_t epoch, int rows_per_rank, const int64_t* src_rows, int n_rows,
+                             size_t row_bytes, void* dst, int flags, void* stream);
+
+/* out[0] = 1 if a peer wait of this process timed out (0 otherwise), out[1] = the peer rank waited for,
+ * out[2] = the event number, out[3] = milliseconds waited.  Readable after the failed launch (pinned host memory). */
+int moco_p2p_last_timeout(uint32_t out[4]);
+
 /* Cross-GPU stream-ordered barrier on peer-mapped signal pads (one uint32 slot
  * per writer rank on every rank): every rank stores `epoch` into slot[rank] of
  * every peer's pad (release, system scope), then waits until all `world` slots
  * of its own pad are >= epoch (acquire).  signal_pads_host: HOST array of `world`
  * device pointers to the pads (each >= world * 4 bytes, zero-initialised).
- * `epoch` must increase by 1 per call.  The spin is bounded (traps, never hangs). */
+ * `epoch` must increase by 1 per event.  The wait is bounded in time (see moco_shuffle_gather_sync). */
 int moco_signal_barrier(void* const* signal_pads_host, int world, int rank,
                         uint32_t epoch, void* stream);
 

@@ -109,18 +109,14 @@ class _ShardedNCE(torch.autograd.Function):
                        "moco_nce_shard_stats")
         with prof("stats_exchange_us"):
             if world > 1:
-                sctx.barrier()
-                # pull every rank's [Nq] pairs as 512-byte rows (one warp each)
-                rpr = Nq * 8 // 512 if (Nq * 8) % 512 == 0 else None
-                if rpr:
-                    ms_all = torch.empty(world, Nq, 2, **f32)
-                    _lib.check(lib.moco_shuffle_gather(ms_buf.table, world, rpr, mod._arange(rpr * world, dev).data_ptr(),
-                                                       rpr * world, 512, ms_all.data_ptr(), 0, stream),
-                               "moco_shuffle_gather")
+                # pull every rank's [Nq] pairs as 512-byte rows (one warp each); the "published" event rides in the
+                # same kernel (moco_shuffle_gather_sync)
+                ms_all = torch.empty(world, Nq, 2, **f32)
+                if (Nq * 8) % 512 == 0:
+                    rpr = Nq * 8 // 512
+                    sctx._pull(ms_buf.table, rpr, mod._arange(rpr * world, dev), 512, ms_all.data_ptr(), synced=True)
                 else:                                                             # odd sizes: one row per rank
-                    ms_all = torch.empty(world, Nq, 2, **f32)
-                    _lib.check(lib.moco_shuffle_gather(ms_buf.table, world, 1, mod._arange(world, dev).data_ptr(), world,
-                                                       Nq * 8, ms_all.data_ptr(), 0, stream), "moco_shuffle_gather")
+                    sctx._pull(ms_buf.table, 1, mod._arange(world, dev), Nq * 8, ms_all.data_ptr(), synced=True)
             else:
                 ms_all = ms
         lse, loss_rows, prob_rows = (torch.empty(Nq, **f32) for _ in range(3))

@@ -51,6 +51,10 @@ SIGNATURES = {
     "moco_ema_update": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p]),
     "moco_crop_to_nhwc_bf16": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]),
     "moco_shuffle_gather": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_int, c_size_t, c_void_p, c_int, c_void_p]),
+    "moco_shuffle_gather_sync": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_uint32, c_int, c_void_p, c_int,
+                                         c_size_t, c_void_p, c_int, c_void_p]),
+    "moco_p2p_last_timeout": (c_int, [POINTER(c_uint32)]),
+    "moco_crop_gather_nhwc_bf16": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "moco_signal_barrier": (c_int, [POINTER(c_void_p), c_int, c_int, c_uint32, c_void_p]),
     "moco_p2p_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
     "moco_p2p_open": (c_int, [c_void_p, POINTER(c_void_p)]),
@@ -98,7 +102,7 @@ class _Counting:
     """Thin proxy over the CDLL that counts this library's kernel launches."""
 
     _PER_CALL = {"moco_nce_shard_stats": 3, "moco_nce_shard_merge": 1, "moco_nce_shard_dq": 2,
-                 "moco_nce_shard_dq_finish": 1, "moco_nce_shard_dq_finish_peers": 1, "moco_queue_enqueue_shard": 1, "moco_queue_enqueue": 1, "moco_f32_to_bf16": 1, "moco_shuffle_gather": 1,
+                 "moco_nce_shard_dq_finish": 1, "moco_nce_shard_dq_finish_peers": 1, "moco_queue_enqueue_shard": 1, "moco_queue_enqueue": 1, "moco_f32_to_bf16": 1, "moco_shuffle_gather": 1, "moco_shuffle_gather_sync": 1, "moco_crop_gather_nhwc_bf16": 1,
                  "moco_ema_update": 1, "moco_crop_to_nhwc_bf16": 1,
                  "moco_signal_barrier": 1, "moco_nce_bwd_dense": 1}
 

@@ -455,8 +455,53 @@ int moco_crop_to_nhwc_bf16(const void* src, int src_dtype, long long src_image_s
     return MOCO_OK;
 }
 
+static int shuffle_gather_impl(const void* const* peers, int world, int rows_per_rank, const int64_t* src_rows, int n_rows,
+                               size_t row_bytes, void* dst, int flags, void* stream_, void* const* pads, int rank,
+                               uint32_t epoch);
+
 int moco_shuffle_gather(const void* const* peers, int world, int rows_per_rank, const int64_t* src_rows, int n_rows,
                         size_t row_bytes, void* dst, int flags, void* stream_) {
+    return shuffle_gather_impl(peers, world, rows_per_rank, src_rows, n_rows, row_bytes, dst, flags, stream_, nullptr, 0, 0);
+}
+
+int moco_shuffle_gather_sync(const void* const* peers, void* const* pads, int world, int rank, uint32_t epoch,
+                             int rows_per_rank, const int64_t* src_rows, int n_rows, size_t row_bytes, void* dst,
+                             int flags, void* stream_) {
+    if (!pads || rank < 0 || rank >= world || epoch == 0) {
+        g_err[0] = 0;
+        set_error("moco_shuffle_gather_sync: bad synchronisation argument (rank=%d world=%d epoch=%u)", rank, world, epoch);
+        return MOCO_ERR_INVALID;
+    }
+    return shuffle_gather_impl(peers, world, rows_per_rank, src_rows, n_rows, row_bytes, dst, flags, stream_, pads, rank, epoch);
+}
+
+int moco_p2p_last_timeout(uint32_t out[4]) {
+    g_err[0] = 0;
+    unsigned int* w = p2p_status_words();
+    if (!out || !w) { set_error("moco_p2p_last_timeout: no status block"); return MOCO_ERR_INVALID; }
+    for (int i = 0; i < 4; ++i) out[i] = w[i];
+    return MOCO_OK;
+}
+
+int moco_crop_gather_nhwc_bf16(const void* src, int src_dtype, long long src_image_stride, const int64_t* src_rows,
+                               void* dst, int N, int C, int HW, void* stream_) {
+    g_err[0] = 0;
+    if (N < 0 || !dst || (!src && N) || (src_dtype != MOCO_F32 && src_dtype != MOCO_BF16) || src_image_stride < (long long)C * HW ||
+        (reinterpret_cast<uintptr_t>(src) & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0 ||
+        (src_image_stride & (src_dtype == MOCO_F32 ? 3 : 7)) != 0) {
+        set_error("moco_crop_gather_nhwc_bf16: bad argument");
+        return MOCO_ERR_INVALID;
+    }
+    cudaError_t e = launch_crop_to_nhwc(src, src_dtype, src_image_stride, static_cast<__nv_bfloat16*>(dst), N, C, HW,
+                                        static_cast<cudaStream_t>(stream_), src_rows);
+    if (e == cudaErrorNotSupported) { set_error("moco_crop_gather_nhwc_bf16: needs C <= 4 and H*W %% 8 == 0 (C=%d HW=%d)", C, HW); return MOCO_ERR_UNSUPPORTED; }
+    if (e != cudaSuccess) return cuda_fail("crop->nhwc kernel", e);
+    return MOCO_OK;
+}
+
+static int shuffle_gather_impl(const void* const* peers, int world, int rows_per_rank, const int64_t* src_rows, int n_rows,
+                               size_t row_bytes, void* dst, int flags, void* stream_, void* const* pads, int rank,
+                               uint32_t epoch) {
     g_err[0] = 0;
     if (!peers || !src_rows || !dst || world < 1 || world > 16 || rows_per_rank < 1 || n_rows < 0 ||
         row_bytes == 0 || (row_bytes & 15) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0) {
@@ -470,7 +515,7 @@ int moco_shuffle_gather(const void* const* peers, int world, int rows_per_rank, 
             return MOCO_ERR_INVALID;
         }
     cudaError_t e = launch_gather(peers, world, rows_per_rank, src_rows, n_rows, row_bytes, dst, flags,
-                                  static_cast<cudaStream_t>(stream_));
+                                  static_cast<cudaStream_t>(stream_), pads, rank, epoch);
     if (e != cudaSuccess) return cuda_fail("shuffle gather kernel", e);
     return MOCO_OK;
 }

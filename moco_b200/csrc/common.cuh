@@ -93,9 +93,11 @@ int ema_chunk_elems();
 cudaError_t launch_ema(const void* segs, const int* chunk_prefix, int n_segs, int n_chunks, float m,
                        float one_minus_m, cudaStream_t stream);
 cudaError_t launch_crop_to_nhwc(const void* src, int src_dtype, long long img_stride, __nv_bfloat16* dst, int N, int C,
-                                int HW, cudaStream_t stream);
+                                int HW, cudaStream_t stream, const int64_t* src_rows = nullptr);
 cudaError_t launch_gather(const void* const* peers, int world, int rows_per_rank, const int64_t* src_rows,
-                          int n_rows, size_t row_bytes, void* dst, int flags, cudaStream_t stream);
+                          int n_rows, size_t row_bytes, void* dst, int flags, cudaStream_t stream,
+                          void* const* pads_host = nullptr, int rank = 0, uint32_t epoch = 0);
+unsigned int* p2p_status_words();
 cudaError_t launch_signal_barrier(void* const* pads, int world, int rank, uint32_t epoch, cudaStream_t stream);
 
 // tcgen05 kernels (nce_sm100.cu).  Return cudaErrorNotSupported when the shape is not handled.

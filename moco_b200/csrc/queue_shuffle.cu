@@ -114,7 +114,8 @@ cudaError_t launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, c
 constexpr int kMaxWorld = 16;
 struct PeerTable { const char* base[kMaxWorld]; };
 
-// Small rows (feature vectors): one warp per destination row, 16-byte lanes.
+// Small rows (feature vectors): one warp per destination row, 16-byte lanes.  (Its cross-GPU synchronisation, when
+// requested, happens in the launch wrapper below: see gather_small_sync_kernel.)
 __global__ void gather_small_kernel(PeerTable peers, int rows_per_rank, const int64_t* __restrict__ src_rows,
                                     int n_rows, int vec_per_row, uint4* __restrict__ dst) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -126,15 +127,95 @@ __global__ void gather_small_kernel(PeerTable peers, int rows_per_rank, const in
     for (int v = lane; v < vec_per_row; v += 32) d[v] = src[v];
 }
 
-// Large rows (images): a persistent grid of CTAs walks (row, chunk) work items.  Each item is a
-// kChunk-byte bulk-async copy peer HBM -> smem (cp.async.bulk, completes on an mbarrier) followed by a
-// bulk store smem -> local HBM, kStages deep, issued by ONE thread per CTA: the copy engines move the
-// bytes over NVLink while the SM's warps stay free for a concurrently running kernel.
+// ---- cross-GPU synchronisation folded into the gather kernels ------------------------------------------------
+// Every rank owns a signal pad (one uint32 slot per writer rank, peer-mapped).  "Event" number `epoch`:
+//   signal : slot[rank] of EVERY peer's pad := epoch (release, system scope) -- "my staging buffer is published";
+//   wait   : all `world` slots of MY OWN pad >= epoch (acquire) -- "every peer's buffer is published".
+// With epoch == 0 the kernels skip both (single GPU, or the caller synchronised some other way).
+// The wait is bounded in TIME (%globaltimer): on expiry the thread records {code, peer, epoch, waited ms} in a pinned
+// host word block the host can read afterwards (moco_p2p_last_timeout) and then traps -- a stalled peer (checkpoint on
+// rank 0, dataloader skew, a debugger) gives a diagnosable error instead of an opaque launch failure or a hang.
+struct PadTable { uint32_t* pad[kMaxWorld]; };
+struct SyncArgs {
+    PadTable pads;
+    int world, rank;
+    uint32_t epoch;                 // 0: no synchronisation
+    unsigned long long timeout_ns;
+    unsigned int* status_host;      // pinned, mapped: [0] code, [1] peer, [2] epoch, [3] waited ms
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void peer_signal(const SyncArgs& sa, int p) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(sa.pads.pad[p] + sa.rank), "r"(sa.epoch) : "memory");
+}
+
+__device__ __forceinline__ void peer_wait(const SyncArgs& sa, int p) {
+    const uint32_t* mine = sa.pads.pad[sa.rank] + p;
+    uint32_t v;
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned int polls = 0;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int32_t)(v - sa.epoch) >= 0) return;
+        if ((++polls & 1023u) == 0u) {
+            const unsigned long long waited = globaltimer_ns() - t0;
+            if (waited > sa.timeout_ns) {
+                if (sa.status_host) {
+                    sa.status_host[1] = (unsigned int)p;
+                    sa.status_host[2] = sa.epoch;
+                    sa.status_host[3] = (unsigned int)(waited / 1000000ull);
+                    __threadfence_system();
+                    sa.status_host[0] = 1u;             // MOCO_P2P_TIMEOUT
+                    __threadfence_system();
+                }
+                __trap();
+            }
+        }
+    }
+}
+
+// Small rows with the synchronisation folded in: block 0 publishes the signal, every block waits for all peers.
+__global__ void gather_small_sync_kernel(PeerTable peers, SyncArgs sa, int rows_per_rank,
+                                         const int64_t* __restrict__ src_rows, int n_rows, int vec_per_row,
+                                         uint4* __restrict__ dst) {
+    if (blockIdx.x == 0 && (int)threadIdx.x < sa.world) { __threadfence_system(); peer_signal(sa, threadIdx.x); }
+    if ((int)threadIdx.x < sa.world) peer_wait(sa, threadIdx.x);
+    __syncthreads();
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    int lane = threadIdx.x & 31;
+    long long g = src_rows[row];
+    const uint4* src = reinterpret_cast<const uint4*>(peers.base[g / rows_per_rank]) + (size_t)(g % rows_per_rank) * vec_per_row;
+    uint4* d = dst + (size_t)row * vec_per_row;
+    for (int v = lane; v < vec_per_row; v += 32) d[v] = src[v];
+}
+
+// Stand-alone event (no data movement attached): signal all peers, wait for all peers.
+__global__ void signal_barrier_kernel(SyncArgs sa) {
+    const int p = threadIdx.x;
+    if (p >= sa.world) return;
+    __threadfence_system();
+    peer_signal(sa, p);
+    peer_wait(sa, p);
+}
+
+// Large rows (images): a persistent grid of CTAs walks (row, chunk) work items.  Each item is a kChunk-byte
+// bulk-async copy peer HBM -> smem (cp.async.bulk, completes on an mbarrier) followed by a bulk store smem -> local
+// HBM, issued by ONE elected thread per CTA: the copy engines move the bytes over NVLink while the SM's warps stay
+// free for a concurrently running kernel.  kStages - 1 loads are always in flight; a stage is refilled as soon as
+// the store that drained it has finished READING shared memory (cp.async.bulk.wait_group.read 1: everything but the
+// newest store), not after all outstanding stores (round 1: wait_group.read 0 drained the pipe once per item).
+// Block 0 publishes this rank's signal first; every CTA waits for all peers' signals before its first pull.
 constexpr int kChunk = 32 * 1024;
-constexpr int kStages = 4;
+constexpr int kStages = 6;
 
 __global__ void __launch_bounds__(32)
-gather_bulk_kernel(PeerTable peers, int rows_per_rank, const int64_t* __restrict__ src_rows, int n_rows,
+gather_bulk_kernel(PeerTable peers, SyncArgs sa, int rows_per_rank, const int64_t* __restrict__ src_rows, int n_rows,
                    unsigned long long row_bytes, char* __restrict__ dst) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full[kStages];
@@ -143,47 +224,48 @@ gather_bulk_kernel(PeerTable peers, int rows_per_rank, const int64_t* __restrict
         fence_mbar_init();
     }
     __syncwarp();
-    if (threadIdx.x != 0) return;
+    if (sa.epoch != 0u) {
+        if (blockIdx.x == 0 && (int)threadIdx.x < sa.world) { __threadfence_system(); peer_signal(sa, threadIdx.x); }
+        if ((int)threadIdx.x < sa.world) peer_wait(sa, threadIdx.x);
+        __syncwarp();
+    }
+    if (!elect_one()) return;
     const unsigned long long chunks_per_row = (row_bytes + kChunk - 1) / kChunk;
     const unsigned long long total = chunks_per_row * (unsigned long long)n_rows;
-    // items owned by this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
-    unsigned long long issue = blockIdx.x, drain = blockIdx.x;
-    int n_issued = 0, n_drained = 0;
-    auto item = [&](unsigned long long it, const char*& s, char*& d, uint32_t& bytes) {
-        unsigned long long row = it / chunks_per_row, ch = it % chunks_per_row;
-        long long g = src_rows[row];
-        unsigned long long off = ch * kChunk;
+    const unsigned long long first = blockIdx.x, stride = gridDim.x;
+    const unsigned long long mine = first < total ? (total - first + stride - 1) / stride : 0ull;     // items of this CTA
+    auto item = [&](unsigned long long k, const char*& s, char*& d, uint32_t& bytes) {
+        const unsigned long long it = first + k * stride;
+        const unsigned long long row = it / chunks_per_row, ch = it % chunks_per_row;
+        const long long g = src_rows[row];
+        const unsigned long long off = ch * kChunk;
         bytes = (uint32_t)min((unsigned long long)kChunk, row_bytes - off);
         s = peers.base[g / rows_per_rank] + (unsigned long long)(g % rows_per_rank) * row_bytes + off;
         d = dst + row * row_bytes + off;
     };
-    while (drain < total) {
-        // keep kStages loads in flight
-        while (issue < total && n_issued - n_drained < kStages) {
-            int st = n_issued % kStages;
-            if (n_issued >= kStages) {
-                // the bulk store that last read this stage must have finished reading smem
-                // (in steady state exactly that store is the oldest uncommitted-complete group)
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            }
-            const char* s; char* d; uint32_t bytes;
-            item(issue, s, d, bytes);
-            mbar_arrive_expect_tx(&full[st], bytes);
-            asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                ::"r"(smem_u32(smem + (size_t)st * kChunk)), "l"(s), "r"(bytes), "r"(smem_u32(&full[st])) : "memory");
-            issue += gridDim.x;
-            ++n_issued;
-        }
-        int st = n_drained % kStages;
-        mbar_wait(&full[st], (n_drained / kStages) & 1);
+    auto load = [&](unsigned long long k) {
+        const int st = (int)(k % kStages);
         const char* s; char* d; uint32_t bytes;
-        item(drain, s, d, bytes);
+        item(k, s, d, bytes);
+        mbar_arrive_expect_tx(&full[st], bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(smem + (size_t)st * kChunk)), "l"(s), "r"(bytes), "r"(smem_u32(&full[st])) : "memory");
+    };
+    for (unsigned long long k = 0; k < mine && k < (unsigned long long)(kStages - 1); ++k) load(k);
+    for (unsigned long long k = 0; k < mine; ++k) {
+        const int st = (int)(k % kStages);
+        mbar_wait(&full[st], (uint32_t)((k / kStages) & 1ull));
+        const char* s; char* d; uint32_t bytes;
+        item(k, s, d, bytes);
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                      ::"l"(d), "r"(smem_u32(smem + (size_t)st * kChunk)), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        drain += gridDim.x;
-        ++n_drained;
+        if (k + kStages - 1 < mine) {
+            // the stage item k + kStages - 1 lands in was drained by store k - 1: all but the newest store (k) must have
+            // finished reading shared memory
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            load(k + kStages - 1);
+        }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -206,63 +288,90 @@ gather_ldg_kernel(PeerTable peers, int rows_per_rank, const int64_t* __restrict_
     for (; v < vec_per_row; v += stride) d[v] = src[v];
 }
 
+static unsigned long long barrier_timeout_ns() {
+    static long long v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOCO_BARRIER_TIMEOUT_MS");
+        long long ms = e ? atoll(e) : 0;
+        if (ms <= 0) ms = 120000;                          // two minutes: far above any legitimate skew of a training step
+        v = ms * 1000000ll;
+    }
+    return (unsigned long long)v;
+}
+
+// pinned, device-mapped status words for the timeout diagnosis (one block per process; see moco_p2p_last_timeout)
+unsigned int* p2p_status_words() {
+    static unsigned int* host = nullptr;
+    if (!host) {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, 64, cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess) {
+            host = static_cast<unsigned int*>(p);
+            for (int i = 0; i < 16; ++i) host[i] = 0u;
+        }
+    }
+    return host;
+}
+
+static SyncArgs make_sync(void* const* pads_host, int world, int rank, uint32_t epoch) {
+    SyncArgs sa;
+    for (int i = 0; i < kMaxWorld; ++i) sa.pads.pad[i] = (pads_host && i < world) ? static_cast<uint32_t*>(pads_host[i]) : nullptr;
+    sa.world = world; sa.rank = rank; sa.epoch = pads_host ? epoch : 0u;
+    sa.timeout_ns = barrier_timeout_ns();
+    sa.status_host = p2p_status_words();
+    return sa;
+}
+
+// pads_host == nullptr or epoch == 0: plain gather (no cross-GPU synchronisation inside the kernel)
 cudaError_t launch_gather(const void* const* peers_host, int world, int rows_per_rank, const int64_t* src_rows,
-                          int n_rows, size_t row_bytes, void* dst, int flags, cudaStream_t stream) {
-    if (n_rows == 0) return cudaSuccess;
+                          int n_rows, size_t row_bytes, void* dst, int flags, cudaStream_t stream,
+                          void* const* pads_host, int rank, uint32_t epoch) {
     if (world > kMaxWorld) return cudaErrorInvalidValue;
+    const SyncArgs sa = make_sync(pads_host, world, rank, epoch);
+    if (n_rows == 0) {
+        if (sa.epoch == 0u) return cudaSuccess;
+        signal_barrier_kernel<<<1, 32, 0, stream>>>(sa);   // still a participant of the event
+        return cudaGetLastError();
+    }
     PeerTable t;
     for (int i = 0; i < kMaxWorld; ++i) t.base[i] = i < world ? static_cast<const char*>(peers_host[i]) : nullptr;
     if (row_bytes >= (size_t)kChunk / 2 && (flags & 1)) {
+        if (sa.epoch != 0u) signal_barrier_kernel<<<1, 32, 0, stream>>>(sa);
         unsigned long long vec = row_bytes / 16;
         int gx = (int)((vec + 256 * 4 - 1) / (256 * 4));
         if (gx > 8) gx = 8;
         gather_ldg_kernel<<<dim3(gx, n_rows), 256, 0, stream>>>(t, rows_per_rank, src_rows, n_rows, vec,
                                                                 static_cast<uint4*>(dst));
     } else if (row_bytes >= (size_t)kChunk / 2) {
-        static bool attr_set = false;
+        static bool attr_set[64] = {false};
         const int smem = kStages * kChunk;
-        if (!attr_set) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+        if (!attr_set[dev]) {
             cudaError_t e = cudaFuncSetAttribute(gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return e;
-            attr_set = true;
+            attr_set[dev] = true;
         }
         size_t chunks = (row_bytes + kChunk - 1) / kChunk * (size_t)n_rows;
         int grid = (int)(chunks < 148 ? chunks : 148);
-        gather_bulk_kernel<<<grid, 32, smem, stream>>>(t, rows_per_rank, src_rows, n_rows, row_bytes,
+        gather_bulk_kernel<<<grid, 32, smem, stream>>>(t, sa, rows_per_rank, src_rows, n_rows, row_bytes,
                                                        static_cast<char*>(dst));
     } else {
         int vec = (int)(row_bytes / 16);
         int rows_per_block = 8;
-        gather_small_kernel<<<(n_rows + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, stream>>>(
-            t, rows_per_rank, src_rows, n_rows, vec, static_cast<uint4*>(dst));
+        int blocks = (n_rows + rows_per_block - 1) / rows_per_block;
+        if (sa.epoch != 0u)
+            gather_small_sync_kernel<<<blocks, rows_per_block * 32, 0, stream>>>(t, sa, rows_per_rank, src_rows, n_rows, vec,
+                                                                                static_cast<uint4*>(dst));
+        else
+            gather_small_kernel<<<blocks, rows_per_block * 32, 0, stream>>>(t, rows_per_rank, src_rows, n_rows, vec,
+                                                                           static_cast<uint4*>(dst));
     }
     return cudaGetLastError();
 }
 
-// ---------------------------------------------------------------------------
-// Signal barrier: slot[writer] of every peer's pad := epoch (release, system scope), then wait for
-// all slots of the own pad (acquire).  Bounded spin.
-// ---------------------------------------------------------------------------
-struct PadTable { uint32_t* pad[kMaxWorld]; };
-
-__global__ void signal_barrier_kernel(PadTable pads, int world, int rank, uint32_t epoch) {
-    int p = threadIdx.x;
-    if (p >= world) return;
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pads.pad[p] + rank), "r"(epoch) : "memory");
-    uint32_t v, spins = 0;
-    const uint32_t* mine = pads.pad[rank] + p;
-    do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-        if (++spins > (1u << 28)) __trap();
-    } while ((int32_t)(v - epoch) < 0);
-}
-
 cudaError_t launch_signal_barrier(void* const* pads_host, int world, int rank, uint32_t epoch, cudaStream_t stream) {
     if (world > kMaxWorld) return cudaErrorInvalidValue;
-    PadTable t;
-    for (int i = 0; i < kMaxWorld; ++i) t.pad[i] = i < world ? static_cast<uint32_t*>(pads_host[i]) : nullptr;
-    signal_barrier_kernel<<<1, 32, 0, stream>>>(t, world, rank, epoch);
+    signal_barrier_kernel<<<1, 32, 0, stream>>>(make_sync(pads_host, world, rank, epoch));
     return cudaGetLastError();
 }
 
@@ -280,14 +389,16 @@ namespace moco {
 
 template <int C, typename SrcT>
 __global__ void __launch_bounds__(256)
-crop_to_nhwc_kernel(const SrcT* __restrict__ src, long long img_stride, __nv_bfloat16* __restrict__ dst, int N, int HW) {
+crop_to_nhwc_kernel(const SrcT* __restrict__ src, long long img_stride, __nv_bfloat16* __restrict__ dst, int N, int HW,
+                    const int64_t* __restrict__ src_rows) {
     pdl_launch_dependents();
     pdl_wait();
     const int groups = HW >> 3;                                   // 8-pixel groups per image
     const long long total = (long long)N * groups;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int n = (int)(t / groups), gidx = (int)(t % groups);
-        const SrcT* s = src + (size_t)n * img_stride + (size_t)gidx * 8;
+        // src_rows: output image n is input image src_rows[n] (single-GPU ShuffleBN: the permutation is the address)
+        const SrcT* s = src + (size_t)(src_rows ? src_rows[n] : n) * img_stride + (size_t)gidx * 8;
         float v[C][8];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -316,7 +427,7 @@ crop_to_nhwc_kernel(const SrcT* __restrict__ src, long long img_stride, __nv_bfl
 }
 
 cudaError_t launch_crop_to_nhwc(const void* src, int src_dtype, long long img_stride, __nv_bfloat16* dst, int N, int C,
-                                int HW, cudaStream_t stream) {
+                                int HW, cudaStream_t stream, const int64_t* src_rows) {
     if (N == 0) return cudaSuccess;
     if (C < 1 || C > 4 || (HW & 7) != 0) return cudaErrorNotSupported;
     const long long total = (long long)N * (HW >> 3);
@@ -326,9 +437,9 @@ cudaError_t launch_crop_to_nhwc(const void* src, int src_dtype, long long img_st
     if (C == C_) {                                                                                                    \
         if (src_dtype == 0)                                                                                           \
             return launch_pdl(crop_to_nhwc_kernel<C_, float>, dim3((unsigned)blocks), dim3(256), 0, stream,            \
-                              static_cast<const float*>(src), img_stride, dst, N, HW);                                \
+                              static_cast<const float*>(src), img_stride, dst, N, HW, src_rows);                      \
         return launch_pdl(crop_to_nhwc_kernel<C_, __nv_bfloat16>, dim3((unsigned)blocks), dim3(256), 0, stream,        \
-                          static_cast<const __nv_bfloat16*>(src), img_stride, dst, N, HW);                            \
+                          static_cast<const __nv_bfloat16*>(src), img_stride, dst, N, HW, src_rows);                  \
     }
     MOCO_CROP(1) MOCO_CROP(2) MOCO_CROP(3) MOCO_CROP(4)
 #undef MOCO_CROP

@@ -9,10 +9,12 @@ B200-native design: the reference all_gathers every rank's whole batch (W x the
 bytes it needs, plus a zero-fill and a cat of the same size, util.py:55-58) and
 then indexes it.  Here each rank publishes its batch in a peer-mapped staging
 buffer and every rank PULLS exactly the rows its slice of the permutation names,
-straight over NVLink/NVSwitch, with one kernel (``moco_shuffle_gather``): the
-permutation is the address computation.  Peers are synchronised with a
-stream-ordered signal-pad barrier (``moco_signal_barrier``); staging buffers are
-double-buffered so one barrier per shuffle suffices.
+straight over NVLink/NVSwitch, with ONE kernel (``moco_shuffle_gather_sync``): the
+permutation is the address computation, and the cross-GPU "everybody has published"
+event is signalled and awaited inside that same kernel (peer-mapped signal pads,
+time-bounded wait).  Staging buffers are double-buffered so one event per shuffle
+suffices.  On a single GPU the forward permute of the images is folded into the
+crop / cast / layout kernel (``moco_crop_gather_nhwc_bf16``).
 """
 from __future__ import annotations
 
@@ -84,6 +86,17 @@ class _PeerBuffer:
                 self.ptrs[r] = p.value
         self.table = (ctypes.c_void_p * world)(*self.ptrs)
 
+    def release(self):
+        """Unmap the peers' buffers and free this rank's (collective in effect: every rank releases the same buffer at
+        the same point; the caller orders it after the last use with a barrier)."""
+        lib = _lib.load()
+        for r, p in enumerate(self.ptrs):
+            if p is not None and r != self.rank:
+                lib.moco_p2p_close(p)
+        if self.local is not None:
+            lib.moco_p2p_free(self.local)
+        self.ptrs, self.local = [None] * self.world, None
+
     def tensor(self, shape, dtype) -> torch.Tensor:
         """View of the local buffer as a torch tensor (no copy)."""
         numel = 1
@@ -129,6 +142,14 @@ class ShuffleContext:
         bufs = self.staging.get(kind)
         if bufs is None or bufs[0].nbytes < nbytes:
             # (re)allocation is collective: every rank sees the same sizes at the same call
+            if bufs is not None:
+                # nobody may still be pulling from the old buffers: device-side event + host sync, then unmap / free
+                self.barrier()
+                torch.cuda.current_stream().synchronize()
+                if self.world > 1:
+                    dist.barrier(group=self.group)
+                for b in bufs:
+                    b.release()
             bufs = [_PeerBuffer(nbytes, self.rank, self.world, self.group) for _ in range(2)]
             self.staging[kind] = bufs
             self.turn[kind] = 0
@@ -141,6 +162,28 @@ class ShuffleContext:
         self.epoch += 1
         _lib.check(lib.moco_signal_barrier(self.pad.table, self.world, self.rank, self.epoch, _lib.cur_stream()),
                    "moco_signal_barrier")
+
+    def _pull(self, table, n, src_rows, row_bytes, out_ptr, synced: bool):
+        """The P2P pull.  synced=True: the "every peer has published" event rides in the SAME kernel
+        (moco_shuffle_gather_sync) -- no separate barrier launch."""
+        lib = _lib.load()
+        if synced and self.world > 1:
+            self.epoch += 1
+            _lib.check(lib.moco_shuffle_gather_sync(table, self.pad.table, self.world, self.rank, self.epoch, n,
+                                                    src_rows.data_ptr(), src_rows.shape[0], row_bytes, out_ptr,
+                                                    self.gather_flags, _lib.cur_stream()), "moco_shuffle_gather_sync")
+        else:
+            _lib.check(lib.moco_shuffle_gather(table, self.world, n, src_rows.data_ptr(), src_rows.shape[0], row_bytes,
+                                               out_ptr, self.gather_flags, _lib.cur_stream()), "moco_shuffle_gather")
+
+    @staticmethod
+    def last_timeout():
+        """(timed_out, peer, event, waited_ms) of the last peer wait that expired in this process, or None."""
+        lib = _lib.load()
+        out = (ctypes.c_uint32 * 4)()
+        if lib.moco_p2p_last_timeout(out) != 0 or out[0] == 0:
+            return None
+        return {"peer": int(out[1]), "event": int(out[2]), "waited_ms": int(out[3])}
 
     def gather(self, kind: str, x: torch.Tensor, src_rows: torch.Tensor, cast_dtype=None,
                channels_last: bool = False) -> torch.Tensor:
@@ -173,11 +216,8 @@ class ShuffleContext:
             stage = buf.tensor(x.shape, dtype)
             if stage.data_ptr() != x.data_ptr():
                 stage.copy_(x)
-            self.barrier()           # every rank's staging buffer is complete and visible
-            table = buf.table
-        _lib.check(lib.moco_shuffle_gather(table, self.world, n, src_rows.data_ptr(), src_rows.shape[0],
-                                           row_bytes, out.data_ptr(), self.gather_flags, _lib.cur_stream()),
-                   "moco_shuffle_gather")
+            table = buf.table        # "every rank's staging buffer is complete" rides in the pull kernel itself
+        self._pull(table, n, src_rows, row_bytes, out.data_ptr(), synced=True)
         return out
 
     def _gather_nhwc(self, kind: str, x: torch.Tensor, src_rows: torch.Tensor) -> torch.Tensor:
@@ -192,23 +232,18 @@ class ShuffleContext:
         row_bytes = C * H * W * 2
         if row_bytes % 16 != 0:
             raise ValueError(f"moco_b200 shuffle: row size {row_bytes} B is not a multiple of 16")
-        if self.world == 1:                                 # private staging (no peers to publish to)
-            st = self._local_stage.get(kind)
-            if st is None or st.numel() < n * row_bytes:
-                st = self._local_stage[kind] = torch.empty(max(n * row_bytes, 16), dtype=torch.uint8, device=x.device)
-            stage_ptr, table = st.data_ptr(), (ctypes.c_void_p * 1)(st.data_ptr())
-        else:
-            buf = self._staging(kind + "_nhwc", n * row_bytes)
-            stage_ptr, table = buf.local, buf.table
-        _lib.check(lib.moco_crop_to_nhwc_bf16(x.data_ptr(), _lib.dtype_code(x), img_stride, stage_ptr, n, C, H * W,
-                                              _lib.cur_stream()), "moco_crop_to_nhwc_bf16")
-        if self.world > 1:
-            self.barrier()
         out = torch.empty((src_rows.shape[0], C, H, W), dtype=torch.bfloat16, device=x.device,
                           memory_format=torch.channels_last)
-        _lib.check(lib.moco_shuffle_gather(table, self.world, n, src_rows.data_ptr(), src_rows.shape[0],
-                                           row_bytes, out.data_ptr(), self.gather_flags, _lib.cur_stream()),
-                   "moco_shuffle_gather")
+        if self.world == 1:
+            # one GPU: the permutation is just the address computation of the crop / cast / layout pass -- ONE kernel
+            _lib.check(lib.moco_crop_gather_nhwc_bf16(x.data_ptr(), _lib.dtype_code(x), img_stride, src_rows.data_ptr(),
+                                                      out.data_ptr(), src_rows.shape[0], C, H * W, _lib.cur_stream()),
+                       "moco_crop_gather_nhwc_bf16")
+            return out
+        buf = self._staging(kind + "_nhwc", n * row_bytes)
+        _lib.check(lib.moco_crop_to_nhwc_bf16(x.data_ptr(), _lib.dtype_code(x), img_stride, buf.local, n, C, H * W,
+                                              _lib.cur_stream()), "moco_crop_to_nhwc_bf16")
+        self._pull(buf.table, n, src_rows, row_bytes, out.data_ptr(), synced=True)     # publish + ONE pull kernel
         return out
 
 

@@ -743,7 +743,9 @@ def test_step_with_fused_normalize_and_graphed_tail_matches_plain_step(graph):
         ema = encoders.resnet18(low_dim=128).cuda()
         ema.load_state_dict(model.state_dict())
         contrast = MemoryMoCo(128, 80, 0.07, device_index=fused and graph).cuda()      # K = 80, 16 keys/step: wraps
-        opt = torch.optim.SGD(model.parameters(), lr=0.03, momentum=0.9, weight_decay=1e-4)
+        # a small learning rate: the comparison is about the kernels, not about how fast seven SGD steps on a
+        # 16-image batch amplify rounding-level differences
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4)
         step = MoCoStep(model, ema, contrast, opt, amp_dtype=None, fuse_normalize=fused, graph_tail=fused and graph)
         g = torch.Generator(device="cuda").manual_seed(4)
         out, w_first = [], None
@@ -762,7 +764,7 @@ def test_step_with_fused_normalize_and_graphed_tail_matches_plain_step(graph):
     # same values in, same losses out; the later steps only leave room for the amplification of rounding-level
     # differences by seven SGD steps on a tiny batch (a wrong gradient or ring slot moves the loss by O(1))
     for it, ((l0, p0), (l1, p1)) in enumerate(zip(o0, o1)):
-        tol = 1e-2 if it < 3 else 6e-2
+        tol = 1e-2 if it < 3 else 3e-2
         assert abs(l0 - l1) < tol * max(1.0, abs(l0)), (it, o0, o1)
         assert abs(p0 - p1) < 5 * tol * max(p0, 1e-6) + 1e-6, (it, o0, o1)
     # the queue holds normalised keys in the same slots; the trained weights followed the same trajectory
