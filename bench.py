@@ -53,11 +53,13 @@ def parse():
     return ap.parse_args()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of nce_stats_kernel from the committed
-# `ncu --set full` captures (profiles/r1_final_nce_c2_ncu_metrics.csv, profiles/r1_final_nce_c5_ncu_metrics.csv)
-NCU_TRAFFIC_BYTES = {(256, 128, 16384): 4287232, (512, 256, 262144): 134522880 + 3844352,   # statistics kernel
-                     # one-pass kernel (profiles/r1_onepass_c2_ncu_metrics.csv, r1_onepass_c5_ncu_metrics.csv)
-                     ("onepass", 256, 128, 16384): 4308992, ("onepass", 512, 256, 262144): 134518528 + 3464192}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+# captures of this round (profiles/r2_*_ncu_metrics.csv; tools/gpu_lab.py op_c2 / op_c3 / op_c5 under ncu)
+NCU_TRAFFIC_BYTES = {
+    ("onepass", 256, 128, 16384): 4332544,                       # profiles/r2_head128_c2_ncu_metrics.csv
+    ("onepass", 256, 128, 65536): None,                          # filled from profiles/r2_head128_c3_ncu_metrics.csv
+    ("onepass", 512, 256, 262144): 134541312 + 3316992,          # profiles/r2_head256_c5_ncu_metrics.csv
+}
 
 
 def load_peaks():
@@ -223,7 +225,8 @@ def stress_roofline(peaks, dev):
     a = 2 * flops / (us_one * 1e-6) / 1e12
     return {
         "workload": "BASELINE configs[4]: N=512 feat_dim=256 K=262144 (hot-path kernels alone, queue 134 MB > L2)",
-        "kernel": "nce_dq2_kernel<FUSED> (one sweep: S=q.Queue^T, P=2^(S/T-m), O+=P.Queue, row sums) -> loss + dq",
+        "kernel": "nce_head256_kernel<FUSED> (one sweep on tcgen05: S=q.Queue^T, P=2^(S/T-m), O+=P.Queue, row sums; q half in "
+                  "TMEM / half in smem, three S buffers) -> loss statistics + dq partials; the tail kernel finishes both",
         "bound": "tensor", "achieved": a, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": a / peaks["tf_burst"],
         "us_per_launch": us_one, "algorithmic_flops": 2 * flops, "hbm_GBps": bytes_ / (us_one * 1e-6) / 1e9,
         "traffic": NCU_TRAFFIC_BYTES.get(("onepass", N, C, K)),
@@ -513,17 +516,18 @@ def run_native(args):
     us_main = us_dq if one_pass else us_stats + us_dq
     a_tf = flops / (us_main * 1e-6) / 1e12
     roofline = {
-        "kernel": ("nce_dq2_kernel<FUSED>: one sweep over the queue on tcgen05 (S = q.Queue^T, P = 2^(S/T - m), "
-                   "O += P.Queue, row sums) -> loss statistics + dq" if one_pass else
-                   "nce_stats_kernel + nce_dq2_kernel (two-pass)") + ", timed inside the step",
+        "kernel": ("nce_head128_kernel<FUSED>: one sweep over the queue on tcgen05 (q staged in-kernel, S = q.Queue^T, "
+                   "P = 2^(S/T - m), O += P.Queue, row sums) -> loss statistics + dq partials" if one_pass else
+                   "nce_stats_kernel + nce_head128_kernel (two-pass)") + ", timed inside the step",
         "bound": "tensor", "achieved": a_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
         "frac": a_tf / peaks["tf_sustained"], "peak_source": peaks["source"] + ", sustained bf16",
         "us_per_launch": us_main, "algorithmic_flops": flops, "algorithmic_bytes": bytes_,
         "hbm_GBps": bytes_ / (us_main * 1e-6) / 1e9, "hbm_frac": bytes_ / (us_main * 1e-6) / 1e9 / peaks["hbm_gbs"],
         "traffic": NCU_TRAFFIC_BYTES.get(("onepass", N, C, K)),
         "note": f"ideal time for this shape is {flops / (peaks['tf_sustained'] * 1e12) * 1e6:.1f} us "
-                f"({flops / 1e9:.2f} GFLOP, {bytes_ / 1e6:.1f} MB): two 128-row tiles per CTA, so launch + prologue + "
-                "one pipeline fill dominate; roofline_stress (N=1 runs) is the tensor-bound shape of BASELINE configs[4]",
+                f"({flops / 1e9:.2f} GFLOP, {bytes_ / 1e6:.1f} MB): {-(-K // 128 * ((N + 127) // 128) // 148)} 128-row tile(s) per CTA, "
+                "so launch + prologue + one pipeline fill + the split-K partials dominate; roofline_stress (N=1 runs) is "
+                "the tensor-bound shape of BASELINE configs[4]",
     }
     line = {
         "metric": METRIC, "value": value, "unit": "images/s",

@@ -47,6 +47,8 @@ namespace moco {
 
 #ifdef MOCO_TRACE
 __device__ long long g_h128_trace[4][64][8];
+__device__ unsigned long long g_h128_cta[160][4];      // per CTA: globaltimer at entry / exit, %smid, tiles
+__device__ __forceinline__ unsigned long long h128_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define MOCO_TR(role, tile, slot) do { if (blockIdx.x == 0 && (tile) < 64) g_h128_trace[role][tile][slot] = clock64(); } while (0)
 #else
 #define MOCO_TR(role, tile, slot) do { } while (0)
@@ -79,6 +81,12 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     if (threadIdx.x == 0) MOCO_TR(3, 0, 0);
+#ifdef MOCO_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < 160) {
+        unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_h128_cta[blockIdx.x][0] = h128_gtime(); g_h128_cta[blockIdx.x][2] = smid;
+    }
+#endif
     const int kchunks = a.C >> 6;
     const int NS = a.stages;
     const int tile_bytes = kchunks * kH1Slab;
@@ -395,6 +403,9 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) MOCO_TR(3, 0, 7);
+#ifdef MOCO_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < 160) { g_h128_cta[blockIdx.x][1] = h128_gtime(); g_h128_cta[blockIdx.x][3] = (unsigned long long)ntiles; }
+#endif
     if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
 
@@ -442,6 +453,9 @@ cudaError_t launch_nce_head128(const void* q, int q_dtype, int normalize, const 
 #ifdef MOCO_TRACE
 extern "C" int moco_debug_h128_trace(long long* host_buf) {
     return (int)cudaMemcpyFromSymbol(host_buf, g_h128_trace, sizeof(g_h128_trace));
+}
+extern "C" int moco_debug_h128_cta(unsigned long long* host_buf) {
+    return (int)cudaMemcpyFromSymbol(host_buf, g_h128_cta, sizeof(g_h128_cta));
 }
 #endif
 

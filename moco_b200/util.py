@@ -85,6 +85,7 @@ class _PeerBuffer:
                 _lib.check(lib.moco_p2p_open(h, ctypes.byref(p)), "moco_p2p_open")
                 self.ptrs[r] = p.value
         self.table = (ctypes.c_void_p * world)(*self.ptrs)
+        self._views = {}
 
     def release(self):
         """Unmap the peers' buffers and free this rank's (collective in effect: every rank releases the same buffer at
@@ -96,9 +97,15 @@ class _PeerBuffer:
         if self.local is not None:
             lib.moco_p2p_free(self.local)
         self.ptrs, self.local = [None] * self.world, None
+        self._views = {}
 
     def tensor(self, shape, dtype) -> torch.Tensor:
-        """View of the local buffer as a torch tensor (no copy)."""
+        """View of the local buffer as a torch tensor (no copy; cached per shape / dtype -- building one through
+        __cuda_array_interface__ costs tens of microseconds of host time)."""
+        key = (tuple(shape), dtype)
+        hit = self._views.get(key)
+        if hit is not None:
+            return hit
         numel = 1
         for s in shape:
             numel *= s
@@ -111,7 +118,8 @@ class _PeerBuffer:
         obj.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1",
                                         "data": (self.local, False), "version": 2}
         t = torch.as_tensor(obj, device=f"cuda:{torch.cuda.current_device()}")
-        return t.view(dtype).view(tuple(shape))
+        out = self._views[key] = t.view(dtype).view(tuple(shape))
+        return out
 
 
 class ShuffleContext:

@@ -53,6 +53,21 @@ def main():
              1: "SM g0: waitS gotS ld0done st0 allst stwait arrived", 2: "SM g1: (same)",
              3: ("KERNEL (C<=128): entry pdl_wait_done setup_done q_data q_staged o_full O_written all_done | row 1: S-issuer got q | row 2: rows converted, smem stores issued, fence.proxy.async done"
                  if C <= 128 else "KERNEL: entry setup_done q_staged o_full O_written all_done")}
+    if C <= 128:
+        cta = (ctypes.c_ulonglong * (160 * 4))()
+        assert raw.moco_debug_h128_cta(cta) == 0
+        rows = [(cta[i * 4], cta[i * 4 + 1], cta[i * 4 + 2], cta[i * 4 + 3]) for i in range(160) if cta[i * 4]]
+        t0 = min(r[0] for r in rows)
+        starts = sorted(r[0] - t0 for r in rows)
+        ends = sorted(r[1] - t0 for r in rows)
+        durs = sorted(r[1] - r[0] for r in rows)
+        print(f"CTAs {len(rows)}: entry skew (ns) min/median/max = {starts[0]}/{starts[len(starts) // 2]}/{starts[-1]}; "
+              f"exit (ns after first entry) min/median/max = {ends[0]}/{ends[len(ends) // 2]}/{ends[-1]}; "
+              f"per-CTA duration (ns) min/median/max = {durs[0]}/{durs[len(durs) // 2]}/{durs[-1]}")
+        by_tiles = {}
+        for r in rows:
+            by_tiles.setdefault(int(r[3]), []).append(r[1] - r[0])
+        print("  duration by tiles per CTA:", {k: (min(v), sorted(v)[len(v) // 2], max(v)) for k, v in sorted(by_tiles.items())})
     for r in range(4):
         print(names[r])
         for i in range(min(64, 24)):
