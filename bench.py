@@ -498,6 +498,19 @@ def run_native(args):
 
     shufflebn = sharded = None
     if world > 1:
+        # the one NCCL collective of the step (library DDP, out of scope): the bucketed gradient all-reduce, timed alone
+        n_params = sum(p.numel() for p in model.parameters())
+        gbuf = torch.zeros(n_params, dtype=torch.bfloat16 if args.ddp_bf16 else torch.float32, device=dev)
+
+        def allreduce(k):
+            for _ in range(k):
+                dist.all_reduce(gbuf)
+        allreduce(2)
+        ar_ms = timed(allreduce, 5) / 5
+        ddp_cfg["limiting_collective"] = {
+            "what": "DDP gradient all-reduce (NCCL, overlapped with backward inside the step)", "bytes": gbuf.numel() * gbuf.element_size(),
+            "alone_us": ar_ms * 1e3, "busbw_GBps": 2 * (world - 1) / world * gbuf.numel() * gbuf.element_size() / (ar_ms * 1e-3) / 1e9}
+        del gbuf
         shufflebn = shufflebn_block(x2, epoch, rank, world, dev, nhwc)
         if not args.no_sharded:
             sharded = sharded_block(args, model, model_ema, opt, x1, x2, epoch, rank, world, dev, nhwc, peaks, timed)

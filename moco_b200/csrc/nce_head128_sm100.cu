@@ -48,6 +48,8 @@ namespace moco {
 #ifdef MOCO_TRACE
 __device__ long long g_h128_trace[4][64][8];
 __device__ unsigned long long g_h128_cta[160][4];      // per CTA: globaltimer at entry / exit, %smid, tiles
+__device__ unsigned long long g_moco_evt[64][4];       // per launch: sweep first entry / last exit
+__device__ unsigned int g_moco_launch = 0, g_moco_exits = 0;
 __device__ __forceinline__ unsigned long long h128_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define MOCO_TR(role, tile, slot) do { if (blockIdx.x == 0 && (tile) < 64) g_h128_trace[role][tile][slot] = clock64(); } while (0)
 #else
@@ -86,6 +88,7 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
         unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         g_h128_cta[blockIdx.x][0] = h128_gtime(); g_h128_cta[blockIdx.x][2] = smid;
     }
+    if (threadIdx.x == 0) atomicMin(&g_moco_evt[g_moco_launch & 63u][0], h128_gtime());
 #endif
     const int kchunks = a.C >> 6;
     const int NS = a.stages;
@@ -405,6 +408,11 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
     if (threadIdx.x == 0) MOCO_TR(3, 0, 7);
 #ifdef MOCO_TRACE
     if (threadIdx.x == 0 && blockIdx.x < 160) { g_h128_cta[blockIdx.x][1] = h128_gtime(); g_h128_cta[blockIdx.x][3] = (unsigned long long)ntiles; }
+    if (threadIdx.x == 0) {
+        atomicMax(&g_moco_evt[g_moco_launch & 63u][1], h128_gtime());
+        __threadfence();
+        if (atomicAdd(&g_moco_exits, 1u) == gridDim.x - 1) { g_moco_exits = 0u; __threadfence(); g_moco_launch = g_moco_launch + 1u; }
+    }
 #endif
     if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
 }
@@ -453,6 +461,16 @@ cudaError_t launch_nce_head128(const void* q, int q_dtype, int normalize, const 
 #ifdef MOCO_TRACE
 extern "C" int moco_debug_h128_trace(long long* host_buf) {
     return (int)cudaMemcpyFromSymbol(host_buf, g_h128_trace, sizeof(g_h128_trace));
+}
+extern "C" int moco_debug_evt(unsigned long long* host_buf) {
+    return (int)cudaMemcpyFromSymbol(host_buf, g_moco_evt, sizeof(g_moco_evt));
+}
+extern "C" int moco_debug_evt_reset() {
+    static unsigned long long init[64][4];
+    for (int i = 0; i < 64; ++i) { init[i][0] = ~0ull; init[i][1] = 0; init[i][2] = ~0ull; init[i][3] = 0; }
+    unsigned int z = 0;
+    cudaMemcpyToSymbol(g_moco_launch, &z, sizeof(z));
+    return (int)cudaMemcpyToSymbol(g_moco_evt, init, sizeof(init));
 }
 extern "C" int moco_debug_h128_cta(unsigned long long* host_buf) {
     return (int)cudaMemcpyFromSymbol(host_buf, g_h128_cta, sizeof(g_h128_cta));

@@ -4,6 +4,7 @@ Each rank regenerates EVERY rank's batch from per-rank seeds, so it can evaluate
 reference's all_gather + index ShuffleBN locally and compare its own P2P-pulled result bit for bit.
 Prints one JSON line from rank 0.
 """
+import ctypes
 import json
 import os
 import sys
@@ -175,6 +176,41 @@ def main():
         remote = int(((fwd[rank * n:(rank + 1) * n] // n) != rank).sum())
         res[f"gather_only_bf16_{kname}_us"] = float(ms) * 1e3
         res[f"gather_only_bf16_{kname}_nvlink_GBps"] = remote * 3 * 224 * 224 * 2 / (float(ms) * 1e-3) / 1e9
+    # ---- push vs pull over NVLink, 100 % remote: the same copy kernels with the roles of the pointers swapped
+    #      (pull: source = the next rank's buffer, destination local; push: source local, destination = the next rank's)
+    nxt = (rank + 1) % world
+    big = ctx._staging("pushpull", x.numel() * 2)
+    big2 = ctx._staging("pushpull", x.numel() * 2)
+    ident = torch.arange(n, dtype=torch.long, device=dev)
+    local_src = torch.randn(n, 3, 224, 224, device=dev).bfloat16()
+    row_bytes = 3 * 224 * 224 * 2
+    ctx.barrier()
+    for flags, kname in ((0, "bulk"), (1, "ldg")):
+        for mode in ("pull", "push"):
+            if mode == "pull":
+                table = (ctypes.c_void_p * 1)(big.ptrs[nxt])
+                dst_ptr = out.data_ptr()
+            else:
+                table = (ctypes.c_void_p * 1)(local_src.data_ptr())
+                dst_ptr = big2.ptrs[nxt]
+
+            def call():
+                return lib.moco_shuffle_gather(table, 1, n, ident.data_ptr(), n, row_bytes, dst_ptr, flags,
+                                               torch.cuda.current_stream().cuda_stream)
+            for _ in range(3):
+                call()
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                call()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1) / 20], device=dev)
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            res[f"{mode}_{kname}_all_remote_GBps"] = n * row_bytes / (float(ms) * 1e-3) / 1e9
+            dist.barrier()
     ctx.barrier()
     dist.barrier()
     if rank == 0:

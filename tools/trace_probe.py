@@ -38,7 +38,10 @@ def main():
     wsb = lib.moco_nce_workspace_bytes(N, C, K)
     ws = torch.zeros(wsb + 256, dtype=torch.uint8, device=dev)
     wp = ws.data_ptr() + (-ws.data_ptr()) % 256
-    for _ in range(3):
+    if C <= 128:
+        raw.moco_debug_evt_reset()
+        raw.moco_debug_tail_evt_reset()
+    for _ in range(8 if C <= 128 else 3):
         rc = lib.moco_nce_fwd(q.data_ptr(), k.data_ptr(), 1, queue.data_ptr(), N, C, K, 1 / 0.07, None, lse.data_ptr(),
                               lr.data_ptr(), pr.data_ptr(), lp.data_ptr(), dq.data_ptr(), wp, wsb, flags,
                               torch.cuda.current_stream().cuda_stream)
@@ -54,6 +57,17 @@ def main():
              3: ("KERNEL (C<=128): entry pdl_wait_done setup_done q_data q_staged o_full O_written all_done | row 1: S-issuer got q | row 2: rows converted, smem stores issued, fence.proxy.async done"
                  if C <= 128 else "KERNEL: entry setup_done q_staged o_full O_written all_done")}
     if C <= 128:
+        evt = (ctypes.c_ulonglong * (64 * 4))()
+        assert raw.moco_debug_evt(evt) == 0
+        tev = (ctypes.c_ulonglong * (64 * 4))()
+        assert raw.moco_debug_tail_evt(tev) == 0
+        rows = [[evt[i * 4], evt[i * 4 + 1], tev[i * 4 + 2], tev[i * 4 + 3]] for i in range(8)]
+        print("per launch (ns): sweep window | sweep last exit -> tail go | tail window | tail last exit -> next sweep first entry")
+        for i in range(1, 8):
+            r, nx = rows[i], rows[i + 1] if i + 1 < 8 else None
+            if r[1] == 0:
+                continue
+            print(f"  launch {i}: {r[1] - r[0]:6d} | {r[2] - r[1]:6d} | {r[3] - r[2]:6d} | " + (f"{nx[0] - r[3]:6d}" if nx and nx[1] else "     -"))
         cta = (ctypes.c_ulonglong * (160 * 4))()
         assert raw.moco_debug_h128_cta(cta) == 0
         rows = [(cta[i * 4], cta[i * 4 + 1], cta[i * 4 + 2], cta[i * 4 + 3]) for i in range(160) if cta[i * 4]]
