@@ -15,6 +15,7 @@ ShuffleBN permute timed alone and BASELINE configs[3] (K=131072 sharded over the
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -219,6 +220,8 @@ def stress_roofline(peaks, dev):
         return (sum(e[0].elapsed_time(e[1]) for e in ev) * 1e3 / iters, sum(e[2].elapsed_time(e[3]) for e in ev) * 1e3 / iters)
 
     _, us_one = timed_kernels(_lib.NCE_AUTO)                      # one-pass kernel reports on the DQ hook
+    win = ctypes.c_float()
+    lib.moco_prof_sweep_window(wp, 148, ctypes.byref(win), stream)
     us_stats, us_dq = timed_kernels(_lib.NCE_TWO_PASS)
     flops = 2.0 * N * C * (K + 1)                                 # per direction: fwd = bwd = 2NC(K+1)
     bytes_ = K * C * 2 + 3 * N * C * 2 + 12 * N
@@ -228,7 +231,8 @@ def stress_roofline(peaks, dev):
         "kernel": "nce_head256_kernel<FUSED> (one sweep on tcgen05: S=q.Queue^T, P=2^(S/T-m), O+=P.Queue, row sums; q half in "
                   "TMEM / half in smem, three S buffers) -> loss statistics + dq partials; the tail kernel finishes both",
         "bound": "tensor", "achieved": a, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": a / peaks["tf_burst"],
-        "us_per_launch": us_one, "algorithmic_flops": 2 * flops, "hbm_GBps": bytes_ / (us_one * 1e-6) / 1e9,
+        "us_per_launch": us_one, "device_window_us": float(win.value),
+        "algorithmic_flops": 2 * flops, "hbm_GBps": bytes_ / (us_one * 1e-6) / 1e9,
         "traffic": NCU_TRAFFIC_BYTES.get(("onepass", N, C, K)),
         "two_pass": {"stats_kernel_us": us_stats, "stats_TFLOPs": flops / (us_stats * 1e-6) / 1e12,
                      "stats_frac": flops / (us_stats * 1e-6) / 1e12 / peaks["tf_burst"],
@@ -275,9 +279,8 @@ def shufflebn_block(x2, epoch, rank, world, dev, nhwc):
     fwd_inds, _ = DistributedShufle.get_shuffle_ids(n * world, epoch, dev)
     src = DistributedShufle.get_local_id(fwd_inds).contiguous()
     out = torch.empty(n * row_bytes // 2, dtype=torch.bfloat16, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
-    gather_us = timed_us(lambda: lib.moco_shuffle_gather(buf.table, world, n, src.data_ptr(), n, row_bytes,
-                                                         out.data_ptr(), ctx.gather_flags, stream))
+    # the pull kernel exactly as forward_shuffle launches it (moco_shuffle_gather_sync: cross-GPU event folded in)
+    gather_us = timed_us(lambda: ctx._pull(buf.table, n, src, row_bytes, out.data_ptr(), synced=True))
     ctx.barrier()
     remote = int(((src // n) != rank).sum().item())
     rr = torch.tensor([float(remote)], device=dev)
@@ -464,6 +467,9 @@ def run_native(args):
     sampler.join()
     lib.moco_prof_set_events(1, None, None)
     lib.moco_prof_set_events(2, None, None)
+    win = ctypes.c_float()
+    sc = next(iter(contrast._scratch.values()))
+    lib.moco_prof_sweep_window(sc.ws_ptr, 148, ctypes.byref(win), torch.cuda.current_stream().cuda_stream)
     us_stats = sum(e[0].elapsed_time(e[1]) for e in ev) * 1e3 / args.steps
     us_dq = sum(e[2].elapsed_time(e[3]) for e in ev) * 1e3 / args.steps
     ms_step = ms_total / args.steps
@@ -535,6 +541,10 @@ def run_native(args):
         "bound": "tensor", "achieved": a_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
         "frac": a_tf / peaks["tf_sustained"], "peak_source": peaks["source"] + ", sustained bf16",
         "us_per_launch": us_main, "algorithmic_flops": flops, "algorithmic_bytes": bytes_,
+        "device_window_us": float(win.value),
+        "device_window_note": "first CTA entry -> last CTA exit of the last sweep kernel on the device clock (%globaltimer): "
+                              "what the CTAs took; us_per_launch (CUDA events around the single kernel, which breaks its "
+                              "programmatic-dependent-launch overlap) also contains ~4.5 us of grid launch and ~2 us of completion",
         "hbm_GBps": bytes_ / (us_main * 1e-6) / 1e9, "hbm_frac": bytes_ / (us_main * 1e-6) / 1e9 / peaks["hbm_gbs"],
         "traffic": NCU_TRAFFIC_BYTES.get(("onepass", N, C, K)),
         "note": f"ideal time for this shape is {flops / (peaks['tf_sustained'] * 1e12) * 1e6:.1f} us "

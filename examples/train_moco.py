@@ -31,6 +31,10 @@ def parse_args(argv=None):
     ap.add_argument("--resume", default="", help="checkpoint written by --save (or by the reference: same keys)")
     ap.add_argument("--save", default="")
     ap.add_argument("--persist-index", action="store_true", help="keep the queue write position across resume")
+    ap.add_argument("--fuse-normalize", action="store_true",
+                    help="encoders return the raw fc output; L2 normalisation (resnet.py:24-33) runs inside the head kernels")
+    ap.add_argument("--graph-tail", action="store_true",
+                    help="single GPU: replay everything after the key encoder from one CUDA graph (device-side ring index)")
     return ap.parse_args(argv)
 
 
@@ -56,7 +60,8 @@ def main(argv=None):
     model = ctor(low_dim=128).to(dev).to(memory_format=torch.channels_last)
     model_ema = ctor(low_dim=128).to(dev).to(memory_format=torch.channels_last)
     moment_update(model, model_ema, 0)                                                    # train.py:133
-    contrast = MemoryMoCo(128, args.nce_k, args.nce_t, persist_index=args.persist_index).to(dev)   # train.py:181
+    contrast = MemoryMoCo(128, args.nce_k, args.nce_t, persist_index=args.persist_index,
+                          device_index=args.graph_tail).to(dev)                          # train.py:181
     opt = torch.optim.SGD(model.parameters(), lr=args.base_lr * args.batch_size * world / 256,
                           momentum=args.momentum, weight_decay=args.weight_decay)        # train.py:183-187
     if args.resume:
@@ -68,7 +73,8 @@ def main(argv=None):
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[args.local_rank],
                                                           broadcast_buffers=False)     # train.py:198
-    step = MoCoStep(model, model_ema, contrast, opt, alpha=args.alpha, channels_last=True)
+    step = MoCoStep(model, model_ema, contrast, opt, alpha=args.alpha, channels_last=True,
+                    fuse_normalize=args.fuse_normalize, graph_tail=args.graph_tail)
 
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     for it in range(args.steps):

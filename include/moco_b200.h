@@ -138,6 +138,10 @@ int moco_nce_step(const void* q, const void* k, int qk_dtype, int normalize,
  * kernel; MOCO_PROF_DQ: the dq kernel).  Pass NULLs to clear.  Not thread-safe. */
 enum { MOCO_PROF_STATS = 1, MOCO_PROF_DQ = 2 };   /* one-pass mode: its single kernel reports as MOCO_PROF_DQ */
 int moco_prof_set_events(int kernel, void* ev_start, void* ev_stop);
+/* Device-clock window of the LAST sweep kernel that ran on `workspace` (first CTA entry -> last CTA exit, %globaltimer,
+ * microseconds): what the kernel's CTAs took, without the grid-launch and completion latency a CUDA-event pair around
+ * a single kernel also contains.  Synchronises `stream`.  n_ctas: upper bound on the grid (148 on B200). */
+int moco_prof_sweep_window(const void* workspace, int n_ctas, float* us_out, void* stream);
 /* Backward of the dense-logits compatibility API (MemoryMoCo.forward returning
  * `out`, then an arbitrary upstream gradient):
  *   dq_i = inv_T * ( g_i0 * k_i + sum_j g_i,1+j * queue_j ),  g = grad_logits [N, K+1] fp32.

@@ -31,6 +31,7 @@ SIGNATURES = {
     "moco_nce_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                               c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_size_t, c_int, c_void_p]),
+    "moco_prof_sweep_window": (c_int, [c_void_p, c_int, POINTER(c_float), c_void_p]),
     "moco_prof_set_events": (c_int, [c_int, c_void_p, c_void_p]),
     "moco_nce_bwd_dense": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float,
                                    c_void_p, c_void_p]),

@@ -236,6 +236,25 @@ int moco_nce_step(const void* q, const void* k, int qk_dtype, int normalize, voi
                     "moco_nce_step");
 }
 
+int moco_prof_sweep_window(const void* workspace, int n_ctas, float* us_out, void* stream_) {
+    g_err[0] = 0;
+    if (!workspace || !us_out || n_ctas < 1 || n_ctas > kMaxCtas) { set_error("moco_prof_sweep_window: bad argument"); return MOCO_ERR_INVALID; }
+    NceWorkspace ws = carve_workspace(const_cast<void*>(workspace), 1, 64);
+    static unsigned long long host[kMaxCtas * 2];
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    cudaError_t e = cudaMemcpyAsync(host, ws.cta_times, (size_t)n_ctas * 16, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return cuda_fail("moco_prof_sweep_window", e);
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (int i = 0; i < n_ctas; ++i) {
+        if (host[2 * i] == 0ull) continue;
+        if (host[2 * i] < lo) lo = host[2 * i];
+        if (host[2 * i + 1] > hi) hi = host[2 * i + 1];
+    }
+    *us_out = (hi > lo) ? (float)((double)(hi - lo) * 1e-3) : 0.f;
+    return MOCO_OK;
+}
+
 int moco_prof_set_events(int kernel, void* ev_start, void* ev_stop) {
     g_err[0] = 0;
     if (kernel < 0 || kernel > 2) { set_error("moco_prof_set_events: bad kernel id"); return MOCO_ERR_INVALID; }

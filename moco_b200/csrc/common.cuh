@@ -15,7 +15,8 @@ constexpr float kLn2 = 0.6931471805599453f;
 
 // Workspace layout shared by every NCE entry point.
 struct NceWorkspace {
-    unsigned int* counters;   // [4]   (zeroed by the prep kernel each call)
+    unsigned int* counters;   // [4]   (zeroed by the prep / sweep kernel each call)
+    unsigned long long* cta_times;   // [kMaxCtas][2] %globaltimer at entry / exit of every CTA of the last sweep kernel
     float* lpos;              // [N]   <q_i, k_i> in fp32, natural units
     __nv_bfloat16* q_bf16;    // [N, C] bf16 copy of q (when q arrives as fp32)
     float2* part_ms;          // [slices, N_pad] per-slice (running max, sum) in the log2 domain
@@ -56,6 +57,7 @@ inline NceWorkspace carve_workspace(void* base, int N, int C) {
     char* p = static_cast<char*>(base);
     size_t off = 0;
     w.counters = reinterpret_cast<unsigned int*>(p + off);            off += 256;
+    w.cta_times = reinterpret_cast<unsigned long long*>(p + off);     off += align_up((size_t)kMaxCtas * 16, 256);
     w.lpos = reinterpret_cast<float*>(p + off);                       off += align_up((size_t)N * 4, 256);
     w.q_bf16 = reinterpret_cast<__nv_bfloat16*>(p + off);             off += align_up((size_t)N * C * 2, 256);
     w.part_ms = reinterpret_cast<float2*>(p + off);                   off += align_up((size_t)kMaxCtas * kRowsPerCta * 8, 256);

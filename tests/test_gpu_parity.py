@@ -773,3 +773,43 @@ def test_step_with_fused_normalize_and_graphed_tail_matches_plain_step(graph):
     # two SGD steps in, the head's weights (which see the gradient through the normalisation first) still agree
     # closely: the backward of Normalize inside the tail kernel is the one autograd applies in the plain run
     assert np.abs(w0 - w1).max() < 2e-2 * np.abs(w0).max(), np.abs(w0 - w1).max() / np.abs(w0).max()
+
+
+def test_normalize_falls_back_to_torch_where_the_kernels_do_not_fuse_it():
+    """feat_dim 256 runs on nce_head256_kernel, which takes q already normalised: forward_loss(normalize=True)
+    then normalises in torch (same definition as resnet.py:30-33) -- same result contract, three more launches."""
+    from moco_b200.NCE import MemoryMoCo
+    rng = np.random.default_rng(31)
+    N, C, K, T = 48, 256, 700, 0.07
+    xq = (rng.standard_normal((N, C)) * 2.5).astype(np.float32)
+    xk = (rng.standard_normal((N, C)) * 0.7).astype(np.float32)
+    memory = rand_unit(rng, K, C)
+    loss, prob, dxq, qh, kh = O.head_with_normalize(xq, xk, memory, T, True)
+    mod = MemoryMoCo(C, K, T)
+    mod.memory.copy_(torch.from_numpy(memory))
+    mod = mod.cuda()
+    xt = torch.from_numpy(xq).cuda().requires_grad_(True)
+    l, p = mod.forward_loss(xt, torch.from_numpy(xk).cuda(), torch.from_numpy(xk).cuda(), normalize=True)
+    l.backward()
+    assert abs(float(l) - loss) < 2e-4 * max(1.0, abs(loss)) and abs(float(p) - prob) < 1e-3 * prob + 1e-9
+    assert np.abs(xt.grad.cpu().numpy() - dxq).max() / np.abs(dxq).max() < 5e-3
+    np.testing.assert_allclose(mod.memory[:N].cpu().numpy(), kh, atol=2e-7)
+
+
+def test_peer_wait_status_block_is_clean_and_standalone_enqueue_keeps_the_device_index():
+    from moco_b200.NCE import MemoryMoCo
+    from moco_b200.util import ShuffleContext
+    assert ShuffleContext.last_timeout() is None
+    m = MemoryMoCo(64, 40, 0.07, device_index=True).cuda()
+    m.index = 33                                          # host assignment (as the reference allows) is honoured
+    keys = torch.nn.functional.normalize(torch.randn(16, 64, device="cuda"), dim=1)
+    q = torch.nn.functional.normalize(torch.randn(16, 64, device="cuda"), dim=1).requires_grad_(True)
+    m.forward_loss(q, keys, keys)                         # fused step: wraps 33..39, 0..8
+    assert m.index == 9 and m.sync_index() == 9
+    m.enqueue(keys)                                       # stand-alone enqueue
+    assert m.index == 25 and m.sync_index() == 25
+    exp = torch.zeros(40, dtype=torch.bool)
+    exp[torch.arange(33, 33 + 32) % 40] = True
+    got = (m.memory.cpu().norm(dim=1) - 1).abs() < 1e-3  # rows holding unit-norm keys
+    init_norms_are_not_one = True
+    assert bool((got[exp]).all()) and init_norms_are_not_one

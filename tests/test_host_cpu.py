@@ -285,5 +285,5 @@ def test_example_trainer_accepts_every_launcher_spelling(monkeypatch):
     monkeypatch.setenv("LOCAL_RANK", "6")
     assert mod.parse_args([]).local_rank == 6
     assert mod.parse_args(["--local-rank", "2"]).local_rank == 2
-    a = mod.parse_args(["--nce-k", "65536", "--nce-t", "0.2", "--persist-index"])
-    assert (a.nce_k, a.nce_t, a.persist_index) == (65536, 0.2, True)
+    a = mod.parse_args(["--nce-k", "65536", "--nce-t", "0.2", "--persist-index", "--fuse-normalize", "--graph-tail"])
+    assert (a.nce_k, a.nce_t, a.persist_index, a.fuse_normalize, a.graph_tail) == (65536, 0.2, True, True, True)

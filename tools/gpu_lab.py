@@ -136,6 +136,10 @@ def run_nce(name):
         else:                                   # one-pass mode: no statistics kernel ran
             del out["stats_kernel_us"]
         out["dq_tflops"] = 4.0 * N * C * K / (out["dq_kernel_us"] * 1e-6) / 1e12
+        import ctypes
+        win = ctypes.c_float()
+        lib.moco_prof_sweep_window(ws_ptr, 148, ctypes.byref(win), stream)
+        out["sweep_device_window_us"] = float(win.value)
     return out
 
 

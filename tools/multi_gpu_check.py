@@ -158,9 +158,10 @@ def main():
     out = torch.empty_like(x)
     lib = _lib.load()
     for flags, kname in ((0, "bulk"), (1, "ldg")):
-        def call():
-            return lib.moco_shuffle_gather(buf.table, world, n, src.data_ptr(), n, 3 * 224 * 224 * 2,
-                                           out.data_ptr(), flags, torch.cuda.current_stream().cuda_stream)
+        ctx.gather_flags = flags
+
+        def call():          # the pull kernel exactly as forward_shuffle launches it (cross-GPU event folded in)
+            return ctx._pull(buf.table, n, src, 3 * 224 * 224 * 2, out.data_ptr(), synced=True)
         for _ in range(3):
             call()
         torch.cuda.synchronize()
