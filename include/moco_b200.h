@@ -270,8 +270,9 @@ int moco_crop_gather_nhwc_bf16(const void* src, int src_dtype, long long src_ima
  * needs, util.py:77,91).  row_bytes must be a multiple of 16 and buffers 16-byte
  * aligned.  Synchronisation with the peers (data ready / buffer reusable) is the
  * caller's: moco_signal_barrier.
- * flags: MOCO_GATHER_AUTO = bulk-async (TMA) copies for rows >= 16 KiB, one warp
- * per row below; MOCO_GATHER_LDG = plain 16-byte load/store kernel for large rows.
+ * flags: MOCO_GATHER_AUTO = bulk-async (TMA) copies for rows of 16 KiB .. 400 KiB,
+ * the 16-byte load/store kernel above that (measured faster for fp32 image rows), one
+ * warp per row below; MOCO_GATHER_LDG = always the load/store kernel for large rows.
  * ---------------------------------------------------------------------- */
 enum { MOCO_GATHER_AUTO = 0, MOCO_GATHER_LDG = 1 };
 int moco_shuffle_gather(const void* const* peer_base_host, int world, int rows_per_rank,

@@ -235,8 +235,10 @@ gather_bulk_kernel(PeerTable peers, SyncArgs sa, int rows_per_rank, const int64_
     const unsigned long long first = blockIdx.x, stride = gridDim.x;
     const unsigned long long mine = first < total ? (total - first + stride - 1) / stride : 0ull;     // items of this CTA
     auto item = [&](unsigned long long k, const char*& s, char*& d, uint32_t& bytes) {
+        // chunk-major order: consecutive CTAs work on consecutive ROWS (rows of a shuffled batch live on different
+        // peers), so at any moment the pulls are spread over all source GPUs instead of 148 CTAs draining one row
         const unsigned long long it = first + k * stride;
-        const unsigned long long row = it / chunks_per_row, ch = it % chunks_per_row;
+        const unsigned long long row = it % (unsigned long long)n_rows, ch = it / (unsigned long long)n_rows;
         const long long g = src_rows[row];
         const unsigned long long off = ch * kChunk;
         bytes = (uint32_t)min((unsigned long long)kChunk, row_bytes - off);
@@ -334,7 +336,11 @@ cudaError_t launch_gather(const void* const* peers_host, int world, int rows_per
     }
     PeerTable t;
     for (int i = 0; i < kMaxWorld; ++i) t.base[i] = i < world ? static_cast<const char*>(peers_host[i]) : nullptr;
-    if (row_bytes >= (size_t)kChunk / 2 && (flags & 1)) {
+    // AUTO: bulk-async copies for rows up to ~300 KB (bf16 images: 152.7 vs 157.5 us at 8 GPUs, and one thread per SM
+    // instead of 8 warps), the 16-byte load/store kernel above that (fp32 images, 602 KB rows: 286 vs 342 us) --
+    // profiles/r2_multi_gpu8_check.json
+    const bool use_ldg = (flags & 1) || row_bytes > (size_t)400 * 1024;
+    if (row_bytes >= (size_t)kChunk / 2 && use_ldg) {
         if (sa.epoch != 0u) signal_barrier_kernel<<<1, 32, 0, stream>>>(sa);
         unsigned long long vec = row_bytes / 16;
         int gx = (int)((vec + 256 * 4 - 1) / (256 * 4));
