@@ -58,7 +58,7 @@ def parse():
 # captures of this round (profiles/r2_*_ncu_metrics.csv; tools/gpu_lab.py op_c2 / op_c3 / op_c5 under ncu)
 NCU_TRAFFIC_BYTES = {
     ("onepass", 256, 128, 16384): 4332544,                       # profiles/r2_head128_c2_ncu_metrics.csv
-    ("onepass", 256, 128, 65536): None,                          # filled from profiles/r2_head128_c3_ncu_metrics.csv
+    ("onepass", 256, 128, 65536): 16915200,                      # profiles/r2_head128_c3_ncu_metrics.csv (0 B written: L2)
     ("onepass", 512, 256, 262144): 134541312 + 3316992,          # profiles/r2_head256_c5_ncu_metrics.csv
 }
 

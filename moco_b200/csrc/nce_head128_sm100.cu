@@ -21,7 +21,9 @@
 // Two MMA-issuing threads: a tcgen05.mma costs its issuing thread ~65-80 cycles, so the 8 S + 8 P.V MMAs of a tile
 // keep ONE thread busy ~1,500-1,850 cycles per tile (profiles/r2b_trace_c4.txt) -- more than the 1,024 cycles of
 // tensor work.  Warp 1 issues S, warp 3 issues P.V; S(i+3) overwriting the buffer P.V(i) reads P from is ordered by
-// the s_free mbarrier P.V(i)'s tcgen05.commit arrives on.
+// the second arrival on kv_full[stage of tile i+3], which P.V(i)'s tcgen05.commit provides (see the barrier set-up).
+// (That ~65-80 cycles was itself an artefact: the issuing threads are now chosen with elect.sync -- with a threadIdx
+// predicate ptxas wraps every tcgen05.mma in an elect/branch loop -- and issue is paced by the pipe.)
 //
 // Stabiliser (FUSED = true, no lse yet): the CONSTANT m = log2e / T -- the largest logit a unit-norm query can have
 // against a unit-norm queue row -- so neither a pass over the first S tile (it cost every CTA ~700 cycles of its
@@ -103,8 +105,7 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
     uint64_t* p_full = bars + 2 * NS + 3;                  // [3]
     uint64_t* o_full = bars + 2 * NS + 6;
     uint64_t* q_ready = bars + 2 * NS + 7;
-    uint64_t* s_free = bars + 2 * NS + 8;                  // [3]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 11);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 8);
     float* exch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);     // [3][128] floats
     // profiling hook (moco_prof_sweep_window): this slot is written by this kernel only and read by the host only, so the
     // store may precede griddepcontrol.wait
@@ -130,7 +131,7 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
         // MMA that last read the S/P buffer the tile's S will overwrite -- one wait per tile for the S-issuer instead of
         // two (an mbarrier wait costs its thread ~100-200 cycles even when the phase has long completed)
         for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 2); mbar_init(&kv_empty[s], 1); }
-        for (int b = 0; b < kH1Bufs; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); mbar_init(&s_free[b], 1); }
+        for (int b = 0; b < kH1Bufs; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); }
         mbar_init(o_full, 1);
         mbar_init(q_ready, 16);
         fence_mbar_init();
@@ -198,7 +199,7 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
             const uint64_t vk_desc0 = make_sw128_desc(smem_u32(v_s), 0, 1024);           // tile as K-major B
             constexpr uint64_t kSlabUnits = (uint64_t)(kH1Slab >> 4);
             const uint64_t tile_units = (uint64_t)(tile_bytes >> 4);
-            int s_st = 0; uint32_t s_ph = 0; uint64_t s_vdesc = vk_desc0; uint32_t s_b = 0, s_use = 0;
+            int s_st = 0; uint32_t s_ph = 0; uint64_t s_vdesc = vk_desc0; uint32_t s_b = 0;
             for (int i = 0; i < ntiles; ++i) {
                 MOCO_TR(0, i, 4);
                 mbar_wait(&kv_full[s_st], s_ph);          // tile landed AND P.V(i-3) has consumed P in buffer s_b
@@ -219,7 +220,7 @@ nce_head128_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
                 MOCO_TR(0, i, 7);
                 s_vdesc += tile_units;
                 if (++s_st == NS) { s_st = 0; s_ph ^= 1u; s_vdesc = vk_desc0; }
-                if (++s_b == kH1Bufs) { s_b = 0; ++s_use; }
+                if (++s_b == kH1Bufs) s_b = 0;
             }
         }
     } else if (warp == 3) {

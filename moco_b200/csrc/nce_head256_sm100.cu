@@ -18,7 +18,8 @@
 // THREE S/P buffers (64 + 256 + 3 x 64 = 512 columns) next to six 32 KB ring stages (32 + 6 x 32 + 2 = 226 KB): the
 // chain of one buffer now has three tiles of tensor work to hide behind.  The smem ports carry 32 KB (q half) +
 // 2 x 32 KB (tile, read by both MMAs) + 32 KB (TMA fill) per 1,024 tensor cycles = 125 B/clk.  Two issuing threads
-// (S on warp 1, P.V on warp 3), ordered by the s_free mbarrier.  (A 96-row tile with two buffers was measured first:
+// (S on warp 1, P.V on warp 3); S(i+3) is ordered after P.V(i) by the second arrival on kv_full[stage of tile i+3]
+// that P.V(i)'s tcgen05.commit provides.  (A 96-row tile with two buffers was measured first:
 // 99.7 us, chain-bound at ~2,100 cycles per tile against 1,536 -- profiles/r2d_trace_c5_bn96.txt.)
 //
 // Stabiliser (FUSED): the constant m = log2e / T, see nce_head128_sm100.cu; the tail kernel (nce_tail.cu) detects
@@ -79,11 +80,10 @@ nce_head256_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
     uint64_t* kv_empty = bars + NS;
     uint64_t* s_full = bars + 2 * NS;        // [3]
     uint64_t* p_full = bars + 2 * NS + 3;    // [3]
-    uint64_t* s_free = bars + 2 * NS + 6;    // [3]
-    uint64_t* o_full = bars + 2 * NS + 9;
-    uint64_t* q_ready = bars + 2 * NS + 10;  // q's first 128 columns are in TMEM
-    uint64_t* qhi_full = bars + 2 * NS + 11; // q's remaining columns have landed in smem
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 12);
+    uint64_t* o_full = bars + 2 * NS + 6;
+    uint64_t* q_ready = bars + 2 * NS + 7;   // q's first 128 columns are in TMEM
+    uint64_t* qhi_full = bars + 2 * NS + 8;  // q's remaining columns have landed in smem
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 9);
     float* exch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);     // [3][128] floats
     // profiling hook (moco_prof_sweep_window): this slot is written by this kernel only and read by the host only, so the
     // store may precede griddepcontrol.wait
@@ -109,7 +109,7 @@ nce_head256_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
         // MMA that last read the S/P buffer the tile's S will overwrite -- one wait per tile for the S-issuer instead of
         // two (an mbarrier wait costs its thread ~100-200 cycles even when the phase has long completed)
         for (int s = 0; s < NS; ++s) { mbar_init(&kv_full[s], 2); mbar_init(&kv_empty[s], 1); }
-        for (int b = 0; b < kH2Bufs; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); mbar_init(&s_free[b], 1); }
+        for (int b = 0; b < kH2Bufs; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 8); }
         mbar_init(o_full, 1);
         mbar_init(q_ready, 4);
         mbar_init(qhi_full, 1);
@@ -172,7 +172,7 @@ nce_head256_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
             const uint64_t qh_desc0 = make_sw128_desc(smem_u32(qhi_s), 0, 1024);
             constexpr uint64_t kSlabUnits = (uint64_t)(kH2Slab >> 4), kQSlabUnits = (uint64_t)(kH2QSlab >> 4);
             const uint64_t tile_units = (uint64_t)(tile_bytes >> 4);
-            int s_st = 0; uint32_t s_ph = 0; uint64_t s_vdesc = vk_desc0; uint32_t b = 0, s_use = 0;
+            int s_st = 0; uint32_t s_ph = 0; uint64_t s_vdesc = vk_desc0; uint32_t b = 0;
             for (int i = 0; i < ntiles; ++i) {
                 MOCO_TR(0, i, 4);
                 mbar_wait(&kv_full[s_st], s_ph);          // tile landed AND P.V(i-3) has consumed P in buffer b
@@ -204,7 +204,7 @@ nce_head256_kernel(const __grid_constant__ CUtensorMap tm_queue, const __grid_co
                 MOCO_TR(0, i, 7);
                 s_vdesc += tile_units;
                 if (++s_st == NS) { s_st = 0; s_ph ^= 1u; s_vdesc = vk_desc0; }
-                if (++b == (uint32_t)kH2Bufs) { b = 0; ++s_use; }
+                if (++b == (uint32_t)kH2Bufs) b = 0;
             }
         }
     } else if (warp == 3) {
