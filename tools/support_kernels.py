@@ -4,8 +4,8 @@
     python tools/support_kernels.py [iters]          # prints one JSON line of per-kernel CUDA-event times
 
 Kernels: crop_to_nhwc (256 x 3 of 6 x 224 x 224 fp32 -> bf16 NHWC), gather_bulk (256 bf16 image rows, W = 1),
-gather_small (2048 x 128 fp32 feature rows), enqueue (2048 x 128 into K = 65536), ema_multi (ResNet-50), and the
-head chain at configs[1] / configs[2] (whatever kernels moco_nce_fwd launches).
+gather_small (2048 x 128 fp32 feature rows), gather_ldg (256 fp32 image rows), crop_gather (the W = 1 ShuffleBN
+kernel), enqueue (2048 x 128 into K = 65536), ema_multi (ResNet-50), and the head chain at configs[1] / configs[2] (whatever kernels moco_nce_fwd launches).
 """
 import ctypes
 import json
@@ -46,6 +46,9 @@ def main():
     k_all[65536][:256] = k
     tab1 = (ctypes.c_void_p * 1)(img.data_ptr())
     tab2 = (ctypes.c_void_p * 1)(feats.data_ptr())
+    img32 = six[:, :3].contiguous()
+    img32_out = torch.empty_like(img32)
+    tab3 = (ctypes.c_void_p * 1)(img32.data_ptr())
 
     ops = {
         "crop_to_nhwc (256x3x224x224 f32 crop of a 6-channel batch -> bf16 NHWC)": lambda: crop_to_channels_last_bf16(six[:, 3:]),
@@ -54,6 +57,13 @@ def main():
         "gather_small (2048 f32 feature rows of 512 B)": lambda: _lib.check(lib.moco_shuffle_gather(
             tab2, 1, 2048, perm2.data_ptr(), 2048, 512, feats_out.data_ptr(), 0, stream), "gather"),
         "ema_multi (ResNet-50, 161 tensors, 23.8 M params)": lambda: moment_update(model, ema, 0.999),
+        "gather_ldg (256 f32 image rows of 602112 B, W=1, load/store variant)": lambda: _lib.check(lib.moco_shuffle_gather(
+            tab3, 1, 256, perm.data_ptr(), 256, 3 * 224 * 224 * 4, img32_out.data_ptr(), 1, stream), "gather"),
+        "crop_gather (W=1 ShuffleBN: 256 x 3 of 6 channels f32 -> permuted bf16 NHWC, one kernel)":
+            lambda: _lib.check(lib.moco_crop_gather_nhwc_bf16(six[:, 3:].data_ptr(), _lib.dtype_code(six), six.stride(0),
+                                                              perm.data_ptr(), img_out.data_ptr(), 256, 3, 224 * 224,
+                                                              stream), "crop_gather"),
+        "enqueue (2048 x 128 f32 keys into K=65536, bf16 + f32 queues)": lambda: contrast[65536].enqueue(k_all[65536]),
     }
 
     def head(K):
@@ -83,7 +93,9 @@ def main():
     bytes_ = {"crop": 256 * 3 * 224 * 224 * 6, "gather_bulk": 256 * 3 * 224 * 224 * 2 * 2, "ema": 23770304 * 12}
     res["GBps"] = {"crop_to_nhwc": bytes_["crop"] / res[list(ops)[0]] / 1e3,
                    "gather_bulk": bytes_["gather_bulk"] / res[list(ops)[1]] / 1e3,
-                   "ema_multi": bytes_["ema"] / res[list(ops)[3]] / 1e3}
+                   "ema_multi": bytes_["ema"] / res[list(ops)[3]] / 1e3,
+                   "gather_ldg": bytes_["gather_bulk"] * 2 / res[list(ops)[4]] / 1e3,
+                   "crop_gather": bytes_["crop"] / res[list(ops)[5]] / 1e3}
     res["note"] = "us per call, CUDA events on the launching stream, L2 flushed before every call (host launch included)"
     print(json.dumps(res))
 
