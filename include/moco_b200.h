@@ -235,6 +235,42 @@ int moco_ema_update(const void* segs_dev, const int32_t* chunk_prefix_dev, int n
                     float m, float one_minus_m, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Batch normalisation of the encoders' channels_last bf16 activations with the
+ * block's ReLU and residual add folded in -- the consumer of ShuffleBN's output.
+ * Replaces, at the reference's call sites moco/models/resnet.py:42-63 (BasicBlock),
+ * :74-102 (Bottleneck), :114,156-157 (stem) and :139-143 (downsample), the sequence
+ * nn.BatchNorm2d (training mode) [-> `out += residual`] [-> nn.ReLU]: per-channel
+ * mean and biased variance over the M = N*H*W rows,
+ *     y = relu?( (x - mean) * rsqrt(var + eps) * gamma + beta  [+ residual] ),
+ * running_mean / running_var updated with `momentum` (unbiased variance), and
+ * num_batches_tracked += 1, as torch.nn.BatchNorm2d does.  Arithmetic in fp32
+ * from the bf16 inputs, one rounding to bf16 on output.
+ *
+ * x, residual, y, dy, dx, dresidual: bf16 [M, C] row-major (= NHWC storage), 16-byte
+ * aligned, C a power of two in [64, 2048].  gamma, beta, running_*, save_*, dgamma,
+ * dbeta: fp32 [C].  num_batches_tracked: int64 scalar on the device.  residual,
+ * running_mean/var (both or neither) and num_batches_tracked may be NULL.
+ * workspace: >= moco_bn_workspace_bytes() bytes, ZEROED ONCE by the caller before
+ * its first use and then private to one stream (the kernels re-arm it).
+ * Two launches per call (reduction + element-wise pass); deterministic.
+ *
+ * moco_bn_bwd: dy is the gradient w.r.t. y.  With g = dy masked by the ReLU
+ * (mask recomputed from x when has_residual == 0, read from y otherwise -- y may be
+ * NULL unless relu && has_residual):  dbeta = sum g,  dgamma = sum g * x^,
+ * dx = gamma * invstd * (g - dbeta / M - x^ * dgamma / M),  dresidual = g (written
+ * only when dresidual != NULL).
+ * ---------------------------------------------------------------------- */
+size_t moco_bn_workspace_bytes(void);
+int moco_bn_fwd_train(const void* x, const void* residual_or_null, void* y, long long M, int C,
+                      const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      long long* num_batches_tracked, float momentum, float eps, int relu,
+                      float* save_mean, float* save_invstd, void* workspace, size_t workspace_bytes, void* stream);
+int moco_bn_bwd(const void* dy, const void* x, const void* y_or_null, long long M, int C,
+                const float* gamma, const float* beta, const float* save_mean, const float* save_invstd,
+                int relu, int has_residual, void* dx, void* dresidual_or_null, float* dgamma, float* dbeta,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
  * Input path: one crop of the [N, C_total, H, W] batch ->
  * bf16 [N, H, W, C] (channels_last storage) in ONE pass.  Replaces the crop
  * split of train.py:250-254 (`torch.split(inputs, [3, 3], dim=1)` + the

@@ -458,6 +458,52 @@ int moco_ema_update(const void* segs, const int32_t* chunk_prefix, int n_segs, i
     return MOCO_OK;
 }
 
+size_t moco_bn_workspace_bytes(void) { return bn_workspace_bytes(); }
+
+static bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
+
+int moco_bn_fwd_train(const void* x, const void* residual, void* y, long long M, int C, const float* gamma,
+                      const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
+                      float momentum, float eps, int relu, float* save_mean, float* save_invstd, void* workspace,
+                      size_t workspace_bytes, void* stream_) {
+    g_err[0] = 0;
+    if (!x || !y || !gamma || !beta || !save_mean || !save_invstd || !workspace || (running_mean == nullptr) != (running_var == nullptr) ||
+        misaligned16(x) || misaligned16(y) || misaligned16(residual) || misaligned16(workspace) || x == y || !(eps > 0.f)) {
+        set_error("moco_bn_fwd_train: bad argument (null / misaligned pointer, in-place, eps <= 0)");
+        return MOCO_ERR_INVALID;
+    }
+    if (workspace_bytes < bn_workspace_bytes()) { set_error("moco_bn_fwd_train: workspace too small"); return MOCO_ERR_WORKSPACE; }
+    cudaError_t e = launch_bn_fwd_train(x, residual, y, M, C, gamma, beta, running_mean, running_var, num_batches_tracked,
+                                        momentum, eps, relu, save_mean, save_invstd, workspace, static_cast<cudaStream_t>(stream_));
+    if (e == cudaErrorNotSupported) {
+        set_error("moco_bn_fwd_train: needs M >= 1 and C a power of two in [64, 2048] (M=%lld C=%d)", M, C);
+        return MOCO_ERR_UNSUPPORTED;
+    }
+    if (e != cudaSuccess) return cuda_fail("batch-norm forward kernels", e);
+    return MOCO_OK;
+}
+
+int moco_bn_bwd(const void* dy, const void* x, const void* y, long long M, int C, const float* gamma, const float* beta,
+                const float* save_mean, const float* save_invstd, int relu, int has_residual, void* dx, void* dresidual,
+                float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, void* stream_) {
+    g_err[0] = 0;
+    if (!dy || !x || !dx || !gamma || !beta || !save_mean || !save_invstd || !dgamma || !dbeta || !workspace ||
+        (relu && has_residual && !y) || misaligned16(dy) || misaligned16(x) || misaligned16(y) || misaligned16(dx) ||
+        misaligned16(dresidual) || misaligned16(workspace)) {
+        set_error("moco_bn_bwd: bad argument (null / misaligned pointer; y is required with relu + residual)");
+        return MOCO_ERR_INVALID;
+    }
+    if (workspace_bytes < bn_workspace_bytes()) { set_error("moco_bn_bwd: workspace too small"); return MOCO_ERR_WORKSPACE; }
+    cudaError_t e = launch_bn_bwd(dy, x, y, M, C, gamma, beta, save_mean, save_invstd, relu, has_residual, dx, dresidual,
+                                  dgamma, dbeta, workspace, static_cast<cudaStream_t>(stream_));
+    if (e == cudaErrorNotSupported) {
+        set_error("moco_bn_bwd: needs M >= 1 and C a power of two in [64, 2048] (M=%lld C=%d)", M, C);
+        return MOCO_ERR_UNSUPPORTED;
+    }
+    if (e != cudaSuccess) return cuda_fail("batch-norm backward kernels", e);
+    return MOCO_OK;
+}
+
 int moco_crop_to_nhwc_bf16(const void* src, int src_dtype, long long src_image_stride, void* dst, int N, int C, int HW,
                            void* stream_) {
     g_err[0] = 0;

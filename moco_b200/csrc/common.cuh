@@ -91,6 +91,13 @@ cudaError_t launch_enqueue(__nv_bfloat16* queue_bf16, float* queue_f32, const vo
                            int n_all, int C, int64_t K, int64_t index, int64_t shard_row0, int64_t shard_rows,
                            cudaStream_t stream);
 cudaError_t launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t stream);
+size_t bn_workspace_bytes();
+cudaError_t launch_bn_fwd_train(const void* x, const void* res, void* y, long long M, int C, const float* gamma,
+                                const float* beta, float* running_mean, float* running_var, long long* nbt, float momentum,
+                                float eps, int relu, float* save_mean, float* save_invstd, void* ws, cudaStream_t stream);
+cudaError_t launch_bn_bwd(const void* dy, const void* x, const void* y, long long M, int C, const float* gamma,
+                          const float* beta, const float* save_mean, const float* save_invstd, int relu, int has_residual,
+                          void* dx, void* dres, float* dgamma, float* dbeta, void* ws, cudaStream_t stream);
 int ema_chunk_elems();
 cudaError_t launch_ema(const void* segs, const int* chunk_prefix, int n_segs, int n_chunks, float m,
                        float one_minus_m, cudaStream_t stream);

@@ -3,13 +3,19 @@
 Plain ResNet-18/34/50 with the MoCo head of the reference's variant
 (``moco/models/resnet.py:109,125-126,177-178``: ``fc`` to ``low_dim`` followed by
 L2 normalisation).  Out of the hot-path scope -- these exist to
-drive the end-to-end step / benchmark; all conv/BN math is cuDNN via PyTorch.
+drive the end-to-end step / benchmark; the convolutions are cuDNN via PyTorch.  The
+BatchNorm -> (+ residual) -> ReLU groups (resnet.py:42-63,74-102,156-157) are
+:class:`moco_b200.bn.BatchNormAct2d`: an ``nn.BatchNorm2d`` (same parameters / buffers /
+state_dict keys) that runs this library's fused channels_last bf16 kernels in training
+mode on CUDA and ``nn.BatchNorm2d``'s own forward everywhere else.
 """
 from __future__ import annotations
 
 import torch
 from torch import nn
 import torch.nn.functional as F
+
+from .bn import BatchNormAct2d
 
 
 class _Basic(nn.Module):
@@ -18,17 +24,16 @@ class _Basic(nn.Module):
     def __init__(self, cin, planes, stride):
         super().__init__()
         self.conv1 = nn.Conv2d(cin, planes, 3, stride, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
+        self.bn1 = BatchNormAct2d(planes, relu=True)
         self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
+        self.bn2 = BatchNormAct2d(planes, relu=True)              # relu(bn(.) + residual)
         self.short = None
         if stride != 1 or cin != planes:
-            self.short = nn.Sequential(nn.Conv2d(cin, planes, 1, stride, bias=False), nn.BatchNorm2d(planes))
+            self.short = nn.Sequential(nn.Conv2d(cin, planes, 1, stride, bias=False), BatchNormAct2d(planes))
 
     def forward(self, x):
-        y = F.relu(self.bn1(self.conv1(x)), inplace=True)
-        y = self.bn2(self.conv2(y))
-        return F.relu(y + (x if self.short is None else self.short(x)), inplace=True)
+        y = self.bn1(self.conv1(x))
+        return self.bn2(self.conv2(y), x if self.short is None else self.short(x))
 
 
 class _Bottleneck(nn.Module):
@@ -38,20 +43,19 @@ class _Bottleneck(nn.Module):
         super().__init__()
         cout = planes * 4
         self.conv1 = nn.Conv2d(cin, planes, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
+        self.bn1 = BatchNormAct2d(planes, relu=True)
         self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
+        self.bn2 = BatchNormAct2d(planes, relu=True)
         self.conv3 = nn.Conv2d(planes, cout, 1, bias=False)
-        self.bn3 = nn.BatchNorm2d(cout)
+        self.bn3 = BatchNormAct2d(cout, relu=True)                # relu(bn(.) + residual)
         self.short = None
         if stride != 1 or cin != cout:
-            self.short = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+            self.short = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), BatchNormAct2d(cout))
 
     def forward(self, x):
-        y = F.relu(self.bn1(self.conv1(x)), inplace=True)
-        y = F.relu(self.bn2(self.conv2(y)), inplace=True)
-        y = self.bn3(self.conv3(y))
-        return F.relu(y + (x if self.short is None else self.short(x)), inplace=True)
+        y = self.bn1(self.conv1(x))
+        y = self.bn2(self.conv2(y))
+        return self.bn3(self.conv3(y), x if self.short is None else self.short(x))
 
 
 class MoCoResNet(nn.Module):
@@ -60,7 +64,8 @@ class MoCoResNet(nn.Module):
     def __init__(self, block, depths, low_dim=128, width=1):
         super().__init__()
         base = int(64 * width)
-        self.stem = nn.Sequential(nn.Conv2d(3, 64, 7, 2, 3, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True),
+        # index 2 was the separate ReLU; kept as a placeholder so that the state_dict keys do not move
+        self.stem = nn.Sequential(nn.Conv2d(3, 64, 7, 2, 3, bias=False), BatchNormAct2d(64, relu=True), nn.Identity(),
                                   nn.MaxPool2d(3, 2, 1))
         layers, cin = [], 64
         for i, d in enumerate(depths):

@@ -287,3 +287,19 @@ def test_example_trainer_accepts_every_launcher_spelling(monkeypatch):
     assert mod.parse_args(["--local-rank", "2"]).local_rank == 2
     a = mod.parse_args(["--nce-k", "65536", "--nce-t", "0.2", "--persist-index", "--fuse-normalize", "--graph-tail"])
     assert (a.nce_k, a.nce_t, a.persist_index, a.fuse_normalize, a.graph_tail) == (65536, 0.2, True, True, True)
+
+
+def test_batchnorm_act_module_is_a_batchnorm2d_off_the_gpu():
+    """BatchNormAct2d away from its kernels (CPU tensors here) = the reference's BatchNorm2d -> += residual -> ReLU
+    (moco/models/resnet.py:96-102), with nn.BatchNorm2d's parameters, buffers and state_dict keys."""
+    import torch.nn.functional as F
+    from moco_b200.bn import BatchNormAct2d
+    torch.manual_seed(0)
+    m, r = BatchNormAct2d(8, relu=True), torch.nn.BatchNorm2d(8)
+    x, res = torch.randn(4, 8, 5, 5), torch.randn(4, 8, 5, 5)
+    assert torch.equal(m(x, res), F.relu(r(x) + res))
+    assert torch.equal(m.running_var, r.running_var) and int(m.num_batches_tracked) == 1
+    assert list(m.state_dict()) == list(r.state_dict())
+    assert isinstance(m, torch.nn.BatchNorm2d)
+    plain = BatchNormAct2d(8)
+    assert torch.equal(plain(x), torch.nn.BatchNorm2d(8)(x))
