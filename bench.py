@@ -45,6 +45,7 @@ def parse():
                     help="encoder activation layout (host PyTorch side)")
     ap.add_argument("--no-stress", action="store_true", help="skip the c5 roofline-stress microbench")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bn-ab", action="store_true", help="N=1: skip the 5 steps timed with ATen's BatchNorm kernels")
     ap.add_argument("--cpu-sample-batch", type=int, default=16,
                     help="images per step of the CPU arm (a bounded sample of the 256-image batch)")
     ap.add_argument("--no-c1", action="store_true", help="reference arm: skip BASELINE configs[0] (R18, K=1024, N=32)")
@@ -502,6 +503,27 @@ def run_native(args):
     h2d = N * 6 * 224 * 224 * 4
     final_loss = sink[-1][0]
 
+    # ---- the same step with the encoders' BatchNorm -> add -> ReLU groups on ATen's kernels instead of this library's
+    #      (moco_b200.bn.set_fused(False)): what csrc/bn_nhwc.cu is worth inside the step.  N = 1 only, 5 steps.
+    encoder_bn = None
+    if world == 1 and not args.no_bn_ab:
+        from moco_b200 import bn as _bn
+        _bn.set_fused(False)
+        try:
+            loop_resident(2)
+            ms_aten = timed(loop_resident, 5) / 5
+        finally:
+            _bn.set_fused(True)
+        loop_resident(1)
+        n_bn = sum(1 for m in model.modules() if isinstance(m, _bn.BatchNormAct2d))
+        encoder_bn = {
+            "kernels": "bn_stats_kernel + bn_apply_kernel (forward, both encoders), bn_bwd_reduce_kernel + bn_bwd_apply_kernel "
+                       "(backward, query encoder): training-mode BatchNorm with the residual add and ReLU folded in, bf16 NHWC",
+            "layers_per_encoder": n_bn, "launches_per_step": 6 * n_bn,
+            "ms_per_step": ms_step, "ms_per_step_aten_batchnorm": ms_aten, "step_speedup": ms_aten / ms_step,
+            "note": "ATen arm = nn.BatchNorm2d's own bf16 channels_last kernels + separate add and ReLU passes, everything "
+                    "else identical (same MoCoStep, same head kernels); profiles/ has the per-kernel ncu captures"}
+
     shufflebn = sharded = None
     if world > 1:
         # the one NCCL collective of the step (library DDP, out of scope): the bucketed gradient all-reduce, timed alone
@@ -570,6 +592,8 @@ def run_native(args):
                           "what": "ShuffleBN fwd/bwd + NHWC publish + dist_collect bit-exact vs the oracle of util.py:47-111; "
                                   "3 sharded-queue steps vs the replicated oracle of Contrast.py:20-34 (all ranks)"}
         line["ddp"] = ddp_cfg
+    if encoder_bn is not None:
+        line["encoder_bn"] = encoder_bn
     if shufflebn is not None:
         line["shufflebn"] = shufflebn
     if sharded is not None:

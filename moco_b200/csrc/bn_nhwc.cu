@@ -35,14 +35,18 @@ constexpr int kBnThreads = 256;
 constexpr int kBnSlab = 64;                          // channels per reduction CTA
 constexpr int kBnLanes = kBnSlab / 8;                // 16-byte vectors per slab row
 constexpr int kBnRows = kBnThreads / kBnLanes;       // rows per pass
-constexpr int kBnUnroll = 4;
 constexpr int kBnMaxSlabs = 32;                      // C <= 2048
 constexpr int kBnPartial = 2 * kBnSlab;              // floats per CTA partial
-// resident CTAs per SM (register budget): statistics 4, forward apply 3, the two backward kernels 2 (three operands and
-// five coefficient sets live per thread); every grid is one resident wave
-constexpr int kBnStatsCtas = 4, kBnApplyCtas = 3, kBnBwdCtas = 2;
+// (16-byte loads in flight per thread and operand, resident CTAs per SM) of each kernel; every grid is one resident
+// wave.  Measured over the 53 layers of ResNet-50 at batch 256 (tools/bn_kernel_times.py, us per encoder pass):
+//   statistics  (4,4) 1652  (8,3) 1748  (8,2) 1610  (2,4) 1773      apply      (4,3) 2527  (4,4) 2372  (8,2) 2145  (2,4) 2531
+//   bwd reduce  (4,2) 2809  (4,3) 4586  (2,4) 3689  (2,3) 3294      bwd apply  (4,2) 4818  (4,3) 6816  (2,4) 5342  (2,3) 4601
+constexpr int kBnStatsUnroll = 8, kBnStatsCtas = 2;
+constexpr int kBnApplyUnroll = 8, kBnApplyCtas = 2;
+constexpr int kBnBwdReduceUnroll = 4, kBnBwdReduceCtas = 2;
+constexpr int kBnBwdApplyUnroll = 2, kBnBwdApplyCtas = 3;
 constexpr int kBnSms = 148;
-constexpr int kBnMaxCtas = kBnSms * kBnStatsCtas;    // workspace sizing
+constexpr int kBnMaxCtas = kBnSms * 4;               // workspace sizing: no reduction grid is larger
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -85,9 +89,11 @@ __device__ __forceinline__ float slab_reduce(float (&acc)[16], float* red /*[8 *
 }
 
 // Publishes this CTA's partial, and in the last CTA of the slab to arrive returns true with the slab totals in
-// tot[128] (same element order as slab_reduce).  Fixed summation order over the R partials.
+// tot[128] (same element order as slab_reduce).  The R partials are added in a fixed order: warp w takes partials
+// w, w + 8, ... (lane l owns floats 4l .. 4l+3 of each, one coalesced 512-byte read per partial, 16 reads in flight),
+// then the 8 warps' sums are added in warp order.
 __device__ __forceinline__ bool slab_finish(float part, float* partial, unsigned int* counter, int slab, int r, int R,
-                                            double* tot /*[256] shared*/, int* flag /*shared*/) {
+                                            double* tot /*[8 * 128] shared*/, int* flag /*shared*/) {
     float* mine = partial + ((size_t)slab * R + r) * kBnPartial;
     if (threadIdx.x < kBnPartial) mine[threadIdx.x] = part;
     __threadfence();
@@ -99,15 +105,30 @@ __device__ __forceinline__ bool slab_finish(float part, float* partial, unsigned
     __syncthreads();
     if (!*flag) return false;
     __threadfence();
-    const int j = threadIdx.x & (kBnPartial - 1), half = threadIdx.x >> 7;
-    const int mid = (R + 1) >> 1;
-    const int r0 = half ? mid : 0, r1 = half ? R : mid;
-    const volatile float* base = partial + (size_t)slab * R * kBnPartial + j;
-    double s = 0.0;
-    for (int q = r0; q < r1; ++q) s += (double)base[(size_t)q * kBnPartial];
-    tot[threadIdx.x] = s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4* base = reinterpret_cast<const float4*>(partial + (size_t)slab * R * kBnPartial) + lane;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    constexpr int kBatch = 16;
+    for (int q0 = warp; q0 < R; q0 += 8 * kBatch) {
+        float4 v[kBatch];
+#pragma unroll
+        for (int t = 0; t < kBatch; ++t) {
+            const int q = q0 + 8 * t;
+            v[t] = (q < R) ? __ldcg(base + (size_t)q * (kBnPartial / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int t = 0; t < kBatch; ++t) { s0 += v[t].x; s1 += v[t].y; s2 += v[t].z; s3 += v[t].w; }
+    }
+    double* mine_tot = tot + warp * kBnPartial + lane * 4;
+    mine_tot[0] = s0; mine_tot[1] = s1; mine_tot[2] = s2; mine_tot[3] = s3;
     __syncthreads();
-    if (threadIdx.x < kBnPartial) tot[threadIdx.x] += tot[threadIdx.x + kBnPartial];
+    if (threadIdx.x < kBnPartial) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += tot[w * kBnPartial + threadIdx.x];
+        __syncwarp();
+        tot[threadIdx.x] = t;                        // warp w' < 4 overwrites only slots its own lanes read last
+    }
     if (threadIdx.x == 0) *counter = 0u;             // re-armed for the next launch on this stream
     __syncthreads();
     return true;
@@ -127,10 +148,11 @@ struct BnStatsArgs {
     long long* num_batches_tracked;  // nullable
 };
 
-__global__ void __launch_bounds__(kBnThreads, kBnStatsCtas)
+template <int kUnroll, int kCtas>
+__global__ void __launch_bounds__(kBnThreads, kCtas)
 bn_stats_kernel(const BnStatsArgs a) {
     __shared__ float red[8 * 128];
-    __shared__ double tot[kBnThreads];
+    __shared__ double tot[8 * kBnPartial];
     __shared__ int flag;
     const int slab = blockIdx.x, r = blockIdx.y;
     const int v = threadIdx.x & (kBnLanes - 1), rl = threadIdx.x >> 3;
@@ -146,18 +168,18 @@ bn_stats_kernel(const BnStatsArgs a) {
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
     const long long p0 = (long long)r * a.ppc;
     const long long p1 = (p0 + a.ppc < a.passes) ? p0 + a.ppc : a.passes;
-    for (long long p = p0; p < p1; p += kBnUnroll) {
-        uint4 u[kBnUnroll];
-        bool live[kBnUnroll];
+    for (long long p = p0; p < p1; p += kUnroll) {
+        uint4 u[kUnroll];
+        bool live[kUnroll];
 #pragma unroll
-        for (int t = 0; t < kBnUnroll; ++t) {
+        for (int t = 0; t < kUnroll; ++t) {
             const long long row = (p + t) * kBnRows + rl;
             live[t] = (p + t < p1) && row < a.M;
             u[t] = make_uint4(0u, 0u, 0u, 0u);
             if (live[t]) u[t] = __ldg(a.x + row * vec_per_row + colv);
         }
 #pragma unroll
-        for (int t = 0; t < kBnUnroll; ++t) {
+        for (int t = 0; t < kUnroll; ++t) {
             if (live[t]) {
                 float f[8];
                 unpack8(u[t], f);
@@ -205,7 +227,8 @@ struct BnApplyArgs {
     const float* beta;
 };
 
-__global__ void __launch_bounds__(kBnThreads, kBnApplyCtas)
+template <int kUnroll, int kCtas>
+__global__ void __launch_bounds__(kBnThreads, kCtas)
 bn_apply_kernel(const BnApplyArgs a) {
     const int lanes = a.C >> 3;                      // a power of two <= 256: this thread's channel group is fixed
     const int v = threadIdx.x & (lanes - 1);
@@ -218,10 +241,10 @@ bn_apply_kernel(const BnApplyArgs a) {
     }
     const long long stride = (long long)gridDim.x * kBnThreads;
     const bool has_res = a.res != nullptr;
-    for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < a.V; i += stride * kBnUnroll) {
-        uint4 u[kBnUnroll], w[kBnUnroll];
+    for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < a.V; i += stride * kUnroll) {
+        uint4 u[kUnroll], w[kUnroll];
 #pragma unroll
-        for (int t = 0; t < kBnUnroll; ++t) {
+        for (int t = 0; t < kUnroll; ++t) {
             const long long j = i + t * stride;
             u[t] = make_uint4(0u, 0u, 0u, 0u);
             w[t] = make_uint4(0u, 0u, 0u, 0u);
@@ -231,7 +254,7 @@ bn_apply_kernel(const BnApplyArgs a) {
             }
         }
 #pragma unroll
-        for (int t = 0; t < kBnUnroll; ++t) {
+        for (int t = 0; t < kUnroll; ++t) {
             const long long j = i + t * stride;
             if (j < a.V) {
                 float f[8], g[8];
@@ -268,10 +291,11 @@ struct BnBwdReduceArgs {
     float* sum_dy_xhat;              // = dgamma
 };
 
-__global__ void __launch_bounds__(kBnThreads, kBnBwdCtas)
+template <int kUnroll, int kCtas>
+__global__ void __launch_bounds__(kBnThreads, kCtas)
 bn_bwd_reduce_kernel(const BnBwdReduceArgs a) {
     __shared__ float red[8 * 128];
-    __shared__ double tot[kBnThreads];
+    __shared__ double tot[8 * kBnPartial];
     __shared__ int flag;
     const int slab = blockIdx.x, r = blockIdx.y;
     const int v = threadIdx.x & (kBnLanes - 1), rl = threadIdx.x >> 3;
@@ -290,11 +314,11 @@ bn_bwd_reduce_kernel(const BnBwdReduceArgs a) {
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
     const long long p0 = (long long)r * a.ppc;
     const long long p1 = (p0 + a.ppc < a.passes) ? p0 + a.ppc : a.passes;
-    for (long long p = p0; p < p1; p += kBnUnroll) {
-        uint4 ud[kBnUnroll], ux[kBnUnroll], uy[kBnUnroll];
-        bool live[kBnUnroll];
+    for (long long p = p0; p < p1; p += kUnroll) {
+        uint4 ud[kUnroll], ux[kUnroll], uy[kUnroll];
+        bool live[kUnroll];
 #pragma unroll
-        for (int t = 0; t < kBnUnroll; ++t) {
+        for (int t = 0; t < kUnroll; ++t) {
             const long long row = (p + t) * kBnRows + rl;
             live[t] = (p + t < p1) && row < a.M;
             ud[t] = ux[t] = uy[t] = make_uint4(0u, 0u, 0u, 0u);
@@ -306,7 +330,7 @@ bn_bwd_reduce_kernel(const BnBwdReduceArgs a) {
             }
         }
 #pragma unroll
-        for (int t = 0; t < kBnUnroll; ++t) {
+        for (int t = 0; t < kUnroll; ++t) {
             if (live[t]) {
                 float d[8], f[8], yy[8];
                 unpack8(ud[t], d);
@@ -351,7 +375,8 @@ struct BnBwdApplyArgs {
     const float* sum_dy_xhat;
 };
 
-__global__ void __launch_bounds__(kBnThreads, kBnBwdCtas)
+template <int kUnroll, int kCtas>
+__global__ void __launch_bounds__(kBnThreads, kCtas)
 bn_bwd_apply_kernel(const BnBwdApplyArgs a) {
     const int lanes = a.C >> 3;
     const int v = threadIdx.x & (lanes - 1);
@@ -371,10 +396,10 @@ bn_bwd_apply_kernel(const BnBwdApplyArgs a) {
         cb[k] = fmaf(-mu, k1, __ldg(a.beta + c));
     }
     const long long stride = (long long)gridDim.x * kBnThreads;
-    for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < a.V; i += stride * kBnUnroll) {
-        uint4 ud[kBnUnroll], ux[kBnUnroll], uy[kBnUnroll];
+    for (long long i = (long long)blockIdx.x * kBnThreads + threadIdx.x; i < a.V; i += stride * kUnroll) {
+        uint4 ud[kUnroll], ux[kUnroll], uy[kUnroll];
 #pragma unroll
-        for (int t = 0; t < kBnUnroll; ++t) {
+        for (int t = 0; t < kUnroll; ++t) {
             const long long j = i + t * stride;
             ud[t] = ux[t] = uy[t] = make_uint4(0u, 0u, 0u, 0u);
             if (j < a.V) {
@@ -384,7 +409,7 @@ bn_bwd_apply_kernel(const BnBwdApplyArgs a) {
             }
         }
 #pragma unroll
-        for (int t = 0; t < kBnUnroll; ++t) {
+        for (int t = 0; t < kUnroll; ++t) {
             const long long j = i + t * stride;
             if (j < a.V) {
                 float d[8], f[8], yy[8], o[8];
@@ -416,24 +441,47 @@ static bool bn_shape_ok(long long M, int C) {
     return (C & (C - 1)) == 0;                       // 64 .. 2048, a power of two (256 % (C / 8) == 0)
 }
 
-static void bn_reduce_plan(long long M, int C, int ctas_per_sm, long long* passes, long long* ppc, int* R) {
+static void bn_reduce_plan(long long M, int C, int unroll, int ctas_per_sm, long long* passes, long long* ppc, int* R) {
     const int slabs = C / kBnSlab;
     const long long np = (M + kBnRows - 1) / kBnRows;
     long long r = kBnSms * ctas_per_sm / slabs;
-    const long long want = (np + kBnUnroll - 1) / kBnUnroll;      // at least one unrolled trip per CTA
+    const long long want = (np + unroll - 1) / unroll;            // at least one unrolled trip per CTA
     if (r > want) r = want;
     if (r < 1) r = 1;
     long long per = (np + r - 1) / r;
-    per = (per + kBnUnroll - 1) / kBnUnroll * kBnUnroll;
+    per = (per + unroll - 1) / unroll * unroll;
     r = (np + per - 1) / per;
     *passes = np; *ppc = per; *R = (int)r;
 }
 
-static int bn_apply_grid(long long V, int ctas_per_sm) {
-    long long g = (V + (long long)kBnThreads * kBnUnroll - 1) / ((long long)kBnThreads * kBnUnroll);
+static int bn_apply_grid(long long V, int unroll, int ctas_per_sm) {
+    long long g = (V + (long long)kBnThreads * unroll - 1) / ((long long)kBnThreads * unroll);
     if (g > kBnSms * ctas_per_sm) g = kBnSms * ctas_per_sm;
     if (g < 1) g = 1;
     return (int)g;
+}
+
+template <int U, int CT>
+static cudaError_t run_stats(BnStatsArgs& s, cudaStream_t stream) {
+    bn_reduce_plan(s.M, s.C, U, CT, &s.passes, &s.ppc, &s.R);
+    bn_stats_kernel<U, CT><<<dim3(s.C / kBnSlab, s.R), kBnThreads, 0, stream>>>(s);
+    return cudaGetLastError();
+}
+template <int U, int CT>
+static cudaError_t run_apply(BnApplyArgs& p, cudaStream_t stream) {
+    bn_apply_kernel<U, CT><<<bn_apply_grid(p.V, U, CT), kBnThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+template <int U, int CT>
+static cudaError_t run_bwd_reduce(BnBwdReduceArgs& s, cudaStream_t stream) {
+    bn_reduce_plan(s.M, s.C, U, CT, &s.passes, &s.ppc, &s.R);
+    bn_bwd_reduce_kernel<U, CT><<<dim3(s.C / kBnSlab, s.R), kBnThreads, 0, stream>>>(s);
+    return cudaGetLastError();
+}
+template <int U, int CT>
+static cudaError_t run_bwd_apply(BnBwdApplyArgs& p, cudaStream_t stream) {
+    bn_bwd_apply_kernel<U, CT><<<bn_apply_grid(p.V, U, CT), kBnThreads, 0, stream>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_bn_fwd_train(const void* x, const void* res, void* y, long long M, int C, const float* gamma,
@@ -443,21 +491,18 @@ cudaError_t launch_bn_fwd_train(const void* x, const void* res, void* y, long lo
     BnStatsArgs s{};
     s.x = static_cast<const uint4*>(x);
     s.M = M; s.C = C;
-    bn_reduce_plan(M, C, kBnStatsCtas, &s.passes, &s.ppc, &s.R);
     s.eps = eps; s.momentum = momentum;
     s.counters = static_cast<unsigned int*>(ws);
     s.partial = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
     s.mean = save_mean; s.invstd = save_invstd;
     s.running_mean = running_mean; s.running_var = running_var; s.num_batches_tracked = nbt;
-    bn_stats_kernel<<<dim3(C / kBnSlab, s.R), kBnThreads, 0, stream>>>(s);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = run_stats<kBnStatsUnroll, kBnStatsCtas>(s, stream);
     if (e != cudaSuccess) return e;
     BnApplyArgs p{};
     p.x = static_cast<const uint4*>(x); p.res = static_cast<const uint4*>(res); p.y = static_cast<uint4*>(y);
     p.V = M * (C >> 3); p.C = C; p.relu = relu;
     p.mean = save_mean; p.invstd = save_invstd; p.gamma = gamma; p.beta = beta;
-    bn_apply_kernel<<<bn_apply_grid(p.V, kBnApplyCtas), kBnThreads, 0, stream>>>(p);
-    return cudaGetLastError();
+    return run_apply<kBnApplyUnroll, kBnApplyCtas>(p, stream);
 }
 
 cudaError_t launch_bn_bwd(const void* dy, const void* x, const void* y, long long M, int C, const float* gamma,
@@ -469,21 +514,18 @@ cudaError_t launch_bn_bwd(const void* dy, const void* x, const void* y, long lon
     BnBwdReduceArgs s{};
     s.dy = static_cast<const uint4*>(dy); s.x = static_cast<const uint4*>(x); s.y = static_cast<const uint4*>(y);
     s.M = M; s.C = C; s.mask = mask;
-    bn_reduce_plan(M, C, kBnBwdCtas, &s.passes, &s.ppc, &s.R);
     s.counters = static_cast<unsigned int*>(ws);
     s.partial = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + 256);
     s.mean = save_mean; s.invstd = save_invstd; s.gamma = gamma; s.beta = beta;
     s.sum_dy = dbeta; s.sum_dy_xhat = dgamma;
-    bn_bwd_reduce_kernel<<<dim3(C / kBnSlab, s.R), kBnThreads, 0, stream>>>(s);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = run_bwd_reduce<kBnBwdReduceUnroll, kBnBwdReduceCtas>(s, stream);
     if (e != cudaSuccess) return e;
     BnBwdApplyArgs p{};
     p.dy = s.dy; p.x = s.x; p.y = s.y; p.dx = static_cast<uint4*>(dx); p.dres = static_cast<uint4*>(dres);
     p.V = M * (C >> 3); p.C = C; p.mask = mask; p.inv_m = (float)(1.0 / (double)M);
     p.mean = save_mean; p.invstd = save_invstd; p.gamma = gamma; p.beta = beta;
     p.sum_dy = dbeta; p.sum_dy_xhat = dgamma;
-    bn_bwd_apply_kernel<<<bn_apply_grid(p.V, kBnBwdCtas), kBnThreads, 0, stream>>>(p);
-    return cudaGetLastError();
+    return run_bwd_apply<kBnBwdApplyUnroll, kBnBwdApplyCtas>(p, stream);
 }
 
 }  // namespace moco
