@@ -271,6 +271,20 @@ int moco_bn_bwd(const void* dy, const void* x, const void* y_or_null, long long 
                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
+ * The stem's max pooling on channels_last bf16 activations.  Replaces
+ * `nn.MaxPool2d(kernel_size=3, stride=2, padding=1)` (moco/models/resnet.py:119,158)
+ * and its backward.  x: bf16 [N, H, W, C] (NHWC storage), C % 8 == 0;
+ * y: bf16 [N, OH, OW, C] with OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+ * taps: uint8 [N, OH, OW, C], the winning tap kh * 3 + kw of every output element
+ * (first maximum in kh-then-kw order, NaN wins -- torch's rule), written by the
+ * forward and consumed by the backward, which adds dy into the winning input
+ * element of every window (gather over the <= 4 windows of a pixel: no atomics,
+ * deterministic).  One launch each.
+ * ---------------------------------------------------------------------- */
+int moco_maxpool3x3s2_fwd(const void* x, void* y, void* taps_u8, int N, int H, int W, int C, void* stream);
+int moco_maxpool3x3s2_bwd(const void* dy, const void* taps_u8, void* dx, int N, int H, int W, int C, void* stream);
+
+/* ------------------------------------------------------------------------
  * Input path: one crop of the [N, C_total, H, W] batch ->
  * bf16 [N, H, W, C] (channels_last storage) in ONE pass.  Replaces the crop
  * split of train.py:250-254 (`torch.split(inputs, [3, 3], dim=1)` + the

@@ -123,3 +123,43 @@ class BatchNormAct2d(nn.BatchNorm2d):
 
     def extra_repr(self):
         return super().extra_repr() + f", relu={self.relu}"
+
+
+class _MaxPool3x3s2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        lib = _lib.load()
+        N, C, H, W = x.shape
+        OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((N, C, OH, OW), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        taps = torch.empty((N, OH, OW, C), dtype=torch.uint8, device=x.device)
+        _lib.check(lib.moco_maxpool3x3s2_fwd(x.data_ptr(), y.data_ptr(), taps.data_ptr(), N, H, W, C, _lib.cur_stream()),
+                   "moco_maxpool3x3s2_fwd")
+        ctx.save_for_backward(taps)
+        ctx.shape = (N, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (taps,) = ctx.saved_tensors
+        N, C, H, W = ctx.shape
+        if dy.dtype != torch.bfloat16:
+            dy = dy.to(torch.bfloat16)
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((N, C, H, W), dtype=torch.bfloat16, device=dy.device, memory_format=torch.channels_last)
+        _lib.check(_lib.load().moco_maxpool3x3s2_bwd(dy.data_ptr(), taps.data_ptr(), dx.data_ptr(), N, H, W, C,
+                                                     _lib.cur_stream()), "moco_maxpool3x3s2_bwd")
+        return dx
+
+
+class MaxPool3x3s2(nn.MaxPool2d):
+    """``nn.MaxPool2d(kernel_size=3, stride=2, padding=1)`` (moco/models/resnet.py:119): this library's kernels for CUDA
+    bf16 channels_last activations, ``nn.MaxPool2d``'s own forward for anything else."""
+
+    def __init__(self):
+        super().__init__(kernel_size=3, stride=2, padding=1)
+
+    def forward(self, x):
+        if _enabled and _rows_ok(x) and x.shape[1] % 8 == 0:
+            return _MaxPool3x3s2Fn.apply(x)
+        return super().forward(x)

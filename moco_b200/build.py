@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmoco_b200.so")
 SOURCES = ["capi.cu", "nce_support.cu", "nce_tail.cu", "nce_sm100.cu", "nce_head128_sm100.cu", "nce_head256_sm100.cu",
-           "queue_shuffle.cu", "ema.cu", "bn_nhwc.cu"]
+           "queue_shuffle.cu", "ema.cu", "bn_nhwc.cu", "pool_nhwc.cu"]
 HEADERS = ["common.cuh", "sm100_ptx.cuh", "tc_common.cuh", "nce_rows.cuh", os.path.join("..", "..", "include", "moco_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -458,6 +458,32 @@ int moco_ema_update(const void* segs, const int32_t* chunk_prefix, int n_segs, i
     return MOCO_OK;
 }
 
+int moco_maxpool3x3s2_fwd(const void* x, void* y, void* taps, int N, int H, int W, int C, void* stream_) {
+    g_err[0] = 0;
+    if (!x || !y || !taps || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) ||
+        (reinterpret_cast<uintptr_t>(taps) & 7)) {
+        set_error("moco_maxpool3x3s2_fwd: null or misaligned pointer");
+        return MOCO_ERR_INVALID;
+    }
+    cudaError_t e = launch_maxpool_fwd(x, y, taps, N, H, W, C, static_cast<cudaStream_t>(stream_));
+    if (e == cudaErrorNotSupported) { set_error("moco_maxpool3x3s2_fwd: needs N, H, W >= 1 and C %% 8 == 0 (C=%d)", C); return MOCO_ERR_UNSUPPORTED; }
+    if (e != cudaSuccess) return cuda_fail("max-pool forward kernel", e);
+    return MOCO_OK;
+}
+
+int moco_maxpool3x3s2_bwd(const void* dy, const void* taps, void* dx, int N, int H, int W, int C, void* stream_) {
+    g_err[0] = 0;
+    if (!dy || !dx || !taps || (reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(dx) & 15) ||
+        (reinterpret_cast<uintptr_t>(taps) & 7)) {
+        set_error("moco_maxpool3x3s2_bwd: null or misaligned pointer");
+        return MOCO_ERR_INVALID;
+    }
+    cudaError_t e = launch_maxpool_bwd(dy, taps, dx, N, H, W, C, static_cast<cudaStream_t>(stream_));
+    if (e == cudaErrorNotSupported) { set_error("moco_maxpool3x3s2_bwd: needs N, H, W >= 1 and C %% 8 == 0 (C=%d)", C); return MOCO_ERR_UNSUPPORTED; }
+    if (e != cudaSuccess) return cuda_fail("max-pool backward kernel", e);
+    return MOCO_OK;
+}
+
 size_t moco_bn_workspace_bytes(void) { return bn_workspace_bytes(); }
 
 static bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; }

@@ -7,7 +7,8 @@ drive the end-to-end step / benchmark; the convolutions are cuDNN via PyTorch.  
 BatchNorm -> (+ residual) -> ReLU groups (resnet.py:42-63,74-102,156-157) are
 :class:`moco_b200.bn.BatchNormAct2d`: an ``nn.BatchNorm2d`` (same parameters / buffers /
 state_dict keys) that runs this library's fused channels_last bf16 kernels in training
-mode on CUDA and ``nn.BatchNorm2d``'s own forward everywhere else.
+mode on CUDA and ``nn.BatchNorm2d``'s own forward everywhere else; the stem's max pooling
+(resnet.py:119) is :class:`moco_b200.bn.MaxPool3x3s2` on the same terms.
 """
 from __future__ import annotations
 
@@ -15,7 +16,7 @@ import torch
 from torch import nn
 import torch.nn.functional as F
 
-from .bn import BatchNormAct2d
+from .bn import BatchNormAct2d, MaxPool3x3s2
 
 
 class _Basic(nn.Module):
@@ -66,7 +67,7 @@ class MoCoResNet(nn.Module):
         base = int(64 * width)
         # index 2 was the separate ReLU; kept as a placeholder so that the state_dict keys do not move
         self.stem = nn.Sequential(nn.Conv2d(3, 64, 7, 2, 3, bias=False), BatchNormAct2d(64, relu=True), nn.Identity(),
-                                  nn.MaxPool2d(3, 2, 1))
+                                  MaxPool3x3s2())
         layers, cin = [], 64
         for i, d in enumerate(depths):
             planes = base * (2 ** i)

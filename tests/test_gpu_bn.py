@@ -174,3 +174,35 @@ def test_cuda_graph_replay():
     z = F.relu(ref(x.float()))
     assert _bad(y.float(), z, 1 / 128, 2e-3) < 1e-5
     assert int(mod.num_batches_tracked) == nbt + 1
+
+
+@pytest.mark.parametrize("N,C,H,W", [(4, 64, 112, 112), (3, 64, 7, 7), (2, 72, 9, 12), (1, 8, 1, 1), (2, 64, 2, 5)])
+def test_maxpool3x3s2_matches_torch_bit_exact(N, C, H, W):
+    """Post-ReLU data (windows full of equal zeros): same maxima, and the gradient goes to the FIRST maximum of each
+    window, as torch.nn.functional.max_pool2d routes it (moco/models/resnet.py:119,158)."""
+    from moco_b200.bn import MaxPool3x3s2
+    import moco_b200._lib as L
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(N * 1000 + H)
+    x = _cl(F.relu(torch.randn(N, C, H, W, device=dev, generator=g)))
+    pool = MaxPool3x3s2()
+    xq = x.clone().requires_grad_(True)
+    before = L.launches
+    y = pool(xq)
+    assert L.launches == before + 1
+    x32 = x.float().requires_grad_(True)
+    z = F.max_pool2d(x32, 3, 2, 1)
+    assert y.shape == z.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(y.float(), z)
+    dy = _cl(torch.randn(z.shape, device=dev, generator=g))
+    y.backward(dy)
+    z.backward(dy.float())
+    ref = x32.grad.bfloat16()
+    # same winner everywhere; where two or more windows route into one pixel the fp32 sums may be added in another order
+    assert float((xq.grad != ref).float().mean()) < 1e-4
+    assert bool(((xq.grad.float() - ref.float()).abs() <= ref.float().abs() / 64 + 1e-6).all())
+    assert torch.equal(xq.grad == 0, ref == 0)
+    # fp32 / NCHW input: nn.MaxPool2d's own path
+    before = L.launches
+    assert torch.equal(pool(x.float()), z.detach())
+    assert L.launches == before
