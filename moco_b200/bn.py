@@ -108,6 +108,7 @@ class BatchNormAct2d(nn.BatchNorm2d):
         return (_enabled and self.training and self.affine and self.momentum is not None
                 and _rows_ok(x) and (residual is None or _rows_ok(residual, x))
                 and 64 <= C <= 2048 and (C & (C - 1)) == 0 and x.shape[1] == C
+                and x.numel() // C > 1                 # a single value per channel: nn.BatchNorm2d's own error
                 and self.weight.dtype == torch.float32 and self.weight.is_cuda
                 and (self.running_mean is None or self.running_mean.dtype == torch.float32))
 
