@@ -20,9 +20,10 @@
 // where g = dy masked by the ReLU (the mask is recomputed from x when there is no residual, read from y otherwise).
 //
 // Reductions: a CTA owns a 64-channel slab (128 contiguous bytes of every row = one 16-byte vector per lane of an
-// 8-lane group) and a contiguous range of rows, 32 rows per pass, 4 passes in flight; per-CTA partials go to a small
-// workspace and the LAST CTA of a slab to finish (ticket counter) adds them in a fixed order in fp64 -- deterministic,
-// no atomics on the data.  Sums are taken of (x - x[0, c]) so that the variance does not cancel.
+// 8-lane group) and a contiguous range of rows, 32 rows per pass, 4 or 8 passes in flight (see the table of measured
+// settings below); per-CTA partials go to a small workspace and the LAST CTA of a slab to finish (ticket counter)
+// adds them in a fixed order in fp64 -- deterministic, no atomics on the data.  Sums are taken of (x - x[0, c]) so
+// that the variance does not cancel.
 // Element-wise passes: thread t keeps the coefficients of its 8 channels in registers (its channel group never
 // changes because the grid stride is a multiple of the row length in vectors) and streams 16-byte vectors linearly.
 #include "common.cuh"

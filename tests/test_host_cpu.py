@@ -303,3 +303,28 @@ def test_batchnorm_act_module_is_a_batchnorm2d_off_the_gpu():
     assert isinstance(m, torch.nn.BatchNorm2d)
     plain = BatchNormAct2d(8)
     assert torch.equal(plain(x), torch.nn.BatchNorm2d(8)(x))
+
+
+def test_encoder_layout_is_unchanged_by_the_fused_norm_modules():
+    """The BatchNormAct2d / MaxPool3x3s2 swap keeps ResNet-50's 161 parameter tensors (the EMA pairs of
+    moco/util.py:124-127), their order, and the checkpoint keys of a plain conv / BatchNorm2d network."""
+    from moco_b200 import encoders
+    m = encoders.resnet50(128)
+    assert len(list(m.parameters())) == 161 and sum(p.numel() for p in m.parameters()) == 23770304
+    keys = set(m.state_dict())
+    for k in ("stem.0.weight", "stem.1.running_mean", "stem.1.num_batches_tracked", "layers.0.bn3.weight",
+              "layers.0.short.1.running_var", "layers.15.conv3.weight", "fc.bias"):
+        assert k in keys, k
+    assert not any(k.startswith("stem.2") or k.startswith("stem.3") for k in keys)
+
+
+def test_bn_and_pool_entries_validate_their_arguments_without_a_gpu():
+    from moco_b200 import _lib
+    lib = _lib.load()
+    assert lib.moco_bn_workspace_bytes() >= 256 + 128 * 4
+    rc = lib.moco_bn_fwd_train(None, None, None, 1024, 64, None, None, None, None, None, 0.1, 1e-5, 1, None, None, None, 0, None)
+    assert rc == -1 and b"moco_bn_fwd_train" in lib.moco_last_error()
+    rc = lib.moco_bn_bwd(None, None, None, 1024, 64, None, None, None, None, 1, 1, None, None, None, None, None, 0, None)
+    assert rc == -1 and b"moco_bn_bwd" in lib.moco_last_error()
+    assert lib.moco_maxpool3x3s2_fwd(None, None, None, 1, 8, 8, 64, None) == -1
+    assert lib.moco_maxpool3x3s2_bwd(None, None, None, 1, 8, 8, 64, None) == -1
