@@ -515,12 +515,28 @@ def run_native(args):
         finally:
             _bn.set_fused(True)
         loop_resident(1)
+        # live HBM roofline of the BN kernels inside the step: CUDA events around every fused call of 2 extra steps
+        # (kept out of the timed region above: 640 event records per step would perturb it)
+        _bn._prof = []
+        loop_resident(2)
+        torch.cuda.synchronize()
+        prof, _bn._prof = _bn._prof, None
+        bn_bytes = sum(p[1] for p in prof) / 2
+        bn_us = sum(p[2].elapsed_time(p[3]) for p in prof) * 1e3 / 2
+        fwd_us = sum(p[2].elapsed_time(p[3]) for p in prof if p[0] == "bn_fwd") * 1e3 / 2
         n_bn = sum(1 for m in model.modules() if isinstance(m, _bn.BatchNormAct2d))
         encoder_bn = {
             "kernels": "bn_stats_kernel + bn_apply_kernel (forward, both encoders), bn_bwd_reduce_kernel + bn_bwd_apply_kernel "
                        "(backward, query encoder): training-mode BatchNorm with the residual add and ReLU folded in, bf16 NHWC",
             "layers_per_encoder": n_bn, "launches_per_step": 6 * n_bn,
             "ms_per_step": ms_step, "ms_per_step_aten_batchnorm": ms_aten, "step_speedup": ms_aten / ms_step,
+            "roofline": {"bound": "hbm", "achieved": bn_bytes / (bn_us * 1e-6) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": bn_bytes / (bn_us * 1e-6) / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["source"],
+                         "algorithmic_bytes_per_step": bn_bytes, "us_per_step": bn_us, "forward_us_per_step": fwd_us,
+                         "calls_per_step": len(prof) // 2,
+                         "how": "CUDA events around every moco_bn_fwd_train / moco_bn_bwd call (2 launches each) of 2 extra "
+                                "steps; bytes = 2 B x elements x (statistics 1 + apply 2 [+1 residual]) forward, "
+                                "(reduce 2 [+1 mask] + apply 3 [+1 mask] [+1 d residual]) backward"},
             "note": "ATen arm = nn.BatchNorm2d's own bf16 channels_last kernels + separate add and ReLU passes, everything "
                     "else identical (same MoCoStep, same head kernels); profiles/ has the per-kernel ncu captures"}
 

@@ -19,6 +19,19 @@ from . import _lib
 
 _workspaces = {}
 _enabled = True
+# bench.py's live roofline pass: a list makes every fused call append (kind, algorithmic bytes, start event, end event)
+_prof = None
+
+
+def _timed(kind, nbytes, call):
+    if _prof is None:
+        return call()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = call()
+    e1.record()
+    _prof.append((kind, nbytes, e0, e1))
+    return rc
 
 
 def set_fused(flag: bool) -> None:
@@ -53,14 +66,15 @@ class _BatchNormActFn(torch.autograd.Function):
         mean = torch.empty(C, dtype=torch.float32, device=x.device)
         invstd = torch.empty_like(mean)
         ws = _workspace(x.device)
-        code = lib.moco_bn_fwd_train(
+        # algorithmic bytes: statistics read x; apply reads x (+ residual) and writes y
+        code = _timed("bn_fwd", M * C * 2 * (3 + (residual is not None)), lambda: lib.moco_bn_fwd_train(
             x.data_ptr(), residual.data_ptr() if residual is not None else None, y.data_ptr(), M, C,
             weight.data_ptr(), bias.data_ptr(),
             running_mean.data_ptr() if running_mean is not None else None,
             running_var.data_ptr() if running_var is not None else None,
             num_batches_tracked.data_ptr() if num_batches_tracked is not None else None,
             float(momentum), float(eps), int(relu), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), ws.numel(),
-            _lib.cur_stream())
+            _lib.cur_stream()))
         _lib.check(code, "moco_bn_fwd_train")
         ctx.relu = bool(relu)
         ctx.has_res = residual is not None
@@ -88,10 +102,13 @@ class _BatchNormActFn(torch.autograd.Function):
         dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
         dbeta = torch.empty_like(dgamma)
         ws = _workspace(x.device)
-        code = lib.moco_bn_bwd(dy.data_ptr(), x.data_ptr(), y.data_ptr() if y is not None else None, N * H * W, C,
-                               weight.data_ptr(), bias.data_ptr(), mean.data_ptr(), invstd.data_ptr(), int(ctx.relu),
-                               int(ctx.has_res), dx.data_ptr(), dres_ptr, dgamma.data_ptr(), dbeta.data_ptr(),
-                               ws.data_ptr(), ws.numel(), _lib.cur_stream())
+        # algorithmic bytes: reduce reads dy, x (+ y for the mask); apply reads the same and writes dx (+ d residual)
+        ops = 2 * (2 + (y is not None)) + 1 + (dres_ptr is not None)
+        code = _timed("bn_bwd", N * H * W * C * 2 * ops, lambda: lib.moco_bn_bwd(
+            dy.data_ptr(), x.data_ptr(), y.data_ptr() if y is not None else None, N * H * W, C,
+            weight.data_ptr(), bias.data_ptr(), mean.data_ptr(), invstd.data_ptr(), int(ctx.relu),
+            int(ctx.has_res), dx.data_ptr(), dres_ptr, dgamma.data_ptr(), dbeta.data_ptr(),
+            ws.data_ptr(), ws.numel(), _lib.cur_stream()))
         _lib.check(code, "moco_bn_bwd")
         return dx, dgamma, dbeta, dres, None, None, None, None, None, None
 
