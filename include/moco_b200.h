@@ -270,6 +270,15 @@ int moco_bn_bwd(const void* dy, const void* x, const void* y_or_null, long long 
                 int relu, int has_residual, void* dx, void* dresidual_or_null, float* dgamma, float* dbeta,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same input pass (crop of the [N, C_total >= 3, H, W] batch, optional row permutation, cast to bf16) written in
+ * the layout of a space-to-depth stem: dst = bf16 [N, H/2 + 3, W/2 + 3, 16] with
+ *     dst[n, R, Q, (b * 2 + d) * 3 + c] = src[rows[n], c, 2 (R - 2) + b, 2 (Q - 2) + d]   (0 outside; channels 12..15 = 0)
+ * over which the reference's first convolution (moco/models/resnet.py:112: 7x7, stride 2, padding 3, 3 -> 64) is a
+ * 4x4 / stride 1 / padding 0 convolution with the re-indexed weights w'[o, (b*2+d)*3+c, a, e] = w[o, c, 2a+b-1, 2e+d-1]
+ * (moco_b200/encoders.py:StemConv).  H, W even; src fp32 (8-byte aligned rows) or bf16.  src_rows may be NULL. */
+int moco_crop_s2d_bf16(const void* src, int src_dtype, long long src_image_stride, const int64_t* src_rows_or_null,
+                       void* dst_bf16, int N, int H, int W, void* stream);
+
 /* ------------------------------------------------------------------------
  * The stem's max pooling on channels_last bf16 activations.  Replaces
  * `nn.MaxPool2d(kernel_size=3, stride=2, padding=1)` (moco/models/resnet.py:119,158)

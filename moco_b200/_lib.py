@@ -50,6 +50,7 @@ SIGNATURES = {
     "moco_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "moco_ema_chunk_elems": (c_int, []),
     "moco_ema_update": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p]),
+    "moco_crop_s2d_bf16": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "moco_maxpool3x3s2_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "moco_maxpool3x3s2_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "moco_bn_workspace_bytes": (c_size_t, []),
@@ -111,7 +112,7 @@ class _Counting:
 
     _PER_CALL = {"moco_nce_shard_stats": 3, "moco_nce_shard_merge": 1, "moco_nce_shard_dq": 2,
                  "moco_nce_shard_dq_finish": 1, "moco_nce_shard_dq_finish_peers": 1, "moco_queue_enqueue_shard": 1, "moco_queue_enqueue": 1, "moco_f32_to_bf16": 1, "moco_shuffle_gather": 1, "moco_shuffle_gather_sync": 1, "moco_crop_gather_nhwc_bf16": 1,
-                 "moco_ema_update": 1, "moco_crop_to_nhwc_bf16": 1, "moco_bn_fwd_train": 2, "moco_bn_bwd": 2, "moco_maxpool3x3s2_fwd": 1, "moco_maxpool3x3s2_bwd": 1,
+                 "moco_ema_update": 1, "moco_crop_to_nhwc_bf16": 1, "moco_bn_fwd_train": 2, "moco_bn_bwd": 2, "moco_crop_s2d_bf16": 1, "moco_maxpool3x3s2_fwd": 1, "moco_maxpool3x3s2_bwd": 1,
                  "moco_signal_barrier": 1, "moco_nce_bwd_dense": 1}
 
     def __init__(self, lib):

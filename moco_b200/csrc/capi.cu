@@ -458,6 +458,21 @@ int moco_ema_update(const void* segs, const int32_t* chunk_prefix, int n_segs, i
     return MOCO_OK;
 }
 
+int moco_crop_s2d_bf16(const void* src, int src_dtype, long long src_image_stride, const int64_t* src_rows, void* dst, int N,
+                       int H, int W, void* stream_) {
+    g_err[0] = 0;
+    if (N < 0 || !dst || (!src && N) || (src_dtype != MOCO_F32 && src_dtype != MOCO_BF16) || src_image_stride < 3LL * H * W ||
+        (reinterpret_cast<uintptr_t>(src) & 7) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15) != 0 || (src_image_stride & 1) != 0) {
+        set_error("moco_crop_s2d_bf16: bad argument");
+        return MOCO_ERR_INVALID;
+    }
+    cudaError_t e = launch_crop_to_s2d(src, src_dtype, src_image_stride, static_cast<__nv_bfloat16*>(dst), N, H, W,
+                                       static_cast<cudaStream_t>(stream_), src_rows);
+    if (e == cudaErrorNotSupported) { set_error("moco_crop_s2d_bf16: needs even H, W >= 2 (H=%d W=%d)", H, W); return MOCO_ERR_UNSUPPORTED; }
+    if (e != cudaSuccess) return cuda_fail("crop->space-to-depth kernel", e);
+    return MOCO_OK;
+}
+
 int moco_maxpool3x3s2_fwd(const void* x, void* y, void* taps, int N, int H, int W, int C, void* stream_) {
     g_err[0] = 0;
     if (!x || !y || !taps || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) ||

@@ -93,6 +93,8 @@ cudaError_t launch_enqueue(__nv_bfloat16* queue_bf16, float* queue_f32, const vo
 cudaError_t launch_f32_to_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t stream);
 cudaError_t launch_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, cudaStream_t stream);
 cudaError_t launch_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, cudaStream_t stream);
+cudaError_t launch_crop_to_s2d(const void* src, int src_dtype, long long img_stride, __nv_bfloat16* dst, int N, int H, int W,
+                               cudaStream_t stream, const int64_t* src_rows);
 size_t bn_workspace_bytes();
 cudaError_t launch_bn_fwd_train(const void* x, const void* res, void* y, long long M, int C, const float* gamma,
                                 const float* beta, float* running_mean, float* running_var, long long* nbt, float momentum,

@@ -432,6 +432,68 @@ crop_to_nhwc_kernel(const SrcT* __restrict__ src, long long img_stride, __nv_bfl
     }
 }
 
+// The same crop, written in the layout a space-to-depth stem reads: the reference's first convolution
+// (moco/models/resnet.py:112, 7x7 / stride 2 / pad 3 on 3 channels) equals a 4x4 / stride 1 / pad 0 convolution over
+//     s[n, R, Q, (b * 2 + d) * 3 + c] = x[n, c, 2 (R - 2) + b, 2 (Q - 2) + d]     (0 outside the image; channels 12..15 = 0)
+// with R < H/2 + 3, Q < W/2 + 3 (two zero rows / columns in front, one behind: the 7-tap window padded to 8 taps),
+// and 16 input channels are what cuDNN's sm_100 implicit-GEMM kernels want (C = 3 runs a legacy kernel at 2 % of
+// peak plus channel-padding passes).  One thread per output pixel: 6 coalesced 8-byte (fp32) or 4-byte (bf16) loads,
+// two 16-byte stores.
+template <typename SrcT>
+__global__ void __launch_bounds__(256)
+crop_to_s2d_kernel(const SrcT* __restrict__ src, long long img_stride, __nv_bfloat16* __restrict__ dst, int N, int H, int W,
+                   const int64_t* __restrict__ src_rows) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int R = (H >> 1) + 3, Q = (W >> 1) + 3;
+    const long long total = (long long)N * R * Q;
+    const size_t HW = (size_t)H * W;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(t % Q);
+        const long long t2 = t / Q;
+        const int r = (int)(t2 % R), n = (int)(t2 / R);
+        __align__(16) __nv_bfloat16 o[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o[e] = __float2bfloat16_rn(0.f);
+        const int h0 = 2 * (r - 2), w0 = 2 * (q - 2);
+        if (h0 >= 0 && h0 < H && w0 >= 0 && w0 < W) {
+            const SrcT* s = src + (size_t)(src_rows ? src_rows[n] : n) * img_stride + (size_t)h0 * W + w0;
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float v0, v1;
+                    if constexpr (sizeof(SrcT) == 4) {
+                        const float2 f = *reinterpret_cast<const float2*>(s + (size_t)c * HW + (size_t)b * W);
+                        v0 = f.x; v1 = f.y;
+                    } else {
+                        const __nv_bfloat162 f = *reinterpret_cast<const __nv_bfloat162*>(s + (size_t)c * HW + (size_t)b * W);
+                        v0 = __bfloat162float(f.x); v1 = __bfloat162float(f.y);
+                    }
+                    o[(b * 2 + 0) * 3 + c] = __float2bfloat16_rn(v0);
+                    o[(b * 2 + 1) * 3 + c] = __float2bfloat16_rn(v1);
+                }
+        }
+        uint4* d = reinterpret_cast<uint4*>(dst + (size_t)t * 16);
+        d[0] = reinterpret_cast<const uint4*>(o)[0];
+        d[1] = reinterpret_cast<const uint4*>(o)[1];
+    }
+}
+
+cudaError_t launch_crop_to_s2d(const void* src, int src_dtype, long long img_stride, __nv_bfloat16* dst, int N, int H, int W,
+                               cudaStream_t stream, const int64_t* src_rows) {
+    if (N == 0) return cudaSuccess;
+    if (H < 2 || W < 2 || (H & 1) || (W & 1)) return cudaErrorNotSupported;
+    const long long total = (long long)N * ((H >> 1) + 3) * ((W >> 1) + 3);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (src_dtype == 0)
+        return launch_pdl(crop_to_s2d_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, stream,
+                          static_cast<const float*>(src), img_stride, dst, N, H, W, src_rows);
+    return launch_pdl(crop_to_s2d_kernel<__nv_bfloat16>, dim3((unsigned)blocks), dim3(256), 0, stream,
+                      static_cast<const __nv_bfloat16*>(src), img_stride, dst, N, H, W, src_rows);
+}
+
 cudaError_t launch_crop_to_nhwc(const void* src, int src_dtype, long long img_stride, __nv_bfloat16* dst, int N, int C,
                                 int HW, cudaStream_t stream, const int64_t* src_rows) {
     if (N == 0) return cudaSuccess;

@@ -59,6 +59,28 @@ class _Bottleneck(nn.Module):
         return self.bn3(self.conv3(y), x if self.short is None else self.short(x))
 
 
+class StemConv(nn.Conv2d):
+    """The reference's first convolution (moco/models/resnet.py:112: 3 -> 64, 7x7, stride 2, padding 3, no bias) with
+    the same weight parameter.  Given the usual [N, 3, H, W] input it is that convolution.  Given the 16-channel
+    space-to-depth input that ``moco_crop_s2d_bf16`` writes ([N, 16, H/2+3, W/2+3], see include/moco_b200.h) it runs
+    the EQUIVALENT 4x4 / stride 1 convolution with the weights re-indexed on the fly,
+        w'[o, (b*2+d)*3 + c, a, e] = w[o, c, 2a+b-1, 2e+d-1]        (taps -1 are zero),
+    which is differentiable w.r.t. the 7x7 parameter -- so cuDNN sees 16 input channels (its sm_100 implicit-GEMM
+    kernels) instead of 3 (a legacy kernel at 2 % of peak + channel-padding passes)."""
+
+    def __init__(self):
+        super().__init__(3, 64, 7, 2, 3, bias=False)
+
+    def s2d_weight(self):
+        w8 = F.pad(self.weight, (1, 0, 1, 0)).view(64, 3, 4, 2, 4, 2)          # [o, c, a, b, e, d]
+        return F.pad(w8.permute(0, 3, 5, 1, 2, 4).reshape(64, 12, 4, 4), (0, 0, 0, 0, 0, 4))
+
+    def forward(self, x):
+        if x.shape[1] == 16:
+            return F.conv2d(x, self.s2d_weight(), None, 1, 0)
+        return super().forward(x)
+
+
 class MoCoResNet(nn.Module):
     """ResNet trunk -> global average pool -> fc(low_dim) -> L2 normalise."""
 
@@ -66,7 +88,7 @@ class MoCoResNet(nn.Module):
         super().__init__()
         base = int(64 * width)
         # index 2 was the separate ReLU; kept as a placeholder so that the state_dict keys do not move
-        self.stem = nn.Sequential(nn.Conv2d(3, 64, 7, 2, 3, bias=False), BatchNormAct2d(64, relu=True), nn.Identity(),
+        self.stem = nn.Sequential(StemConv(), BatchNormAct2d(64, relu=True), nn.Identity(),
                                   MaxPool3x3s2())
         layers, cin = [], 64
         for i, d in enumerate(depths):
@@ -79,6 +101,7 @@ class MoCoResNet(nn.Module):
         # l2norm=False: return the raw fc output -- the contrast head then normalises inside its kernels
         # (MemoryMoCo.forward_loss(..., normalize=True))
         self.l2norm = True
+        self.accepts_s2d = True          # forward() also takes moco_crop_s2d_bf16's 16-channel layout (StemConv)
         for m in self.modules():
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")

@@ -22,7 +22,7 @@ import torch
 
 from .NCE import MemoryMoCo
 from .NCE.Contrast import _nce_forward
-from .util import DistributedShufle, _world, crop_to_channels_last_bf16, moment_update, set_bn_train
+from .util import DistributedShufle, _world, crop_to_channels_last_bf16, crop_to_s2d_bf16, moment_update, set_bn_train
 
 
 def _unwrap(m):
@@ -38,6 +38,10 @@ class MoCoStep:
         self.amp_dtype = amp_dtype
         # fused input path only where it is value-preserving: bf16 autocast would round the images identically
         self.nhwc = bool(channels_last) and amp_dtype is torch.bfloat16
+        # ... and in the space-to-depth layout when both stems take it (encoders.StemConv): channels_last="nhwc" keeps
+        # the plain 3-channel NHWC crops
+        self.s2d = (self.nhwc and channels_last != "nhwc" and getattr(_unwrap(model), "accepts_s2d", False)
+                    and getattr(model_ema, "accepts_s2d", False))
         self.side = torch.cuda.Stream() if overlap_shuffle else None
         self.fuse_normalize = bool(fuse_normalize)
         if self.fuse_normalize:
@@ -117,15 +121,18 @@ class MoCoStep:
         """x1, x2: [N, 3, 224, 224] CUDA tensors (the two crops, train.py:250-254).
         Returns (loss, prob) as 0-d CUDA tensors."""
         main = torch.cuda.current_stream()
+        # bf16 NHWC crops; in the space-to-depth layout when both encoders' stems take it and the images allow it
+        layout = self.nhwc and ("s2d" if (self.s2d and x1.shape[1] == 3 and x1.shape[2] % 2 == 0 and x1.shape[3] % 2 == 0)
+                                else True)
         if self.side is not None:
             # ShuffleBN forward (train.py:258) on the side stream while the query encoder runs
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side), torch.no_grad():
                 x2_shuffled, backward_inds = DistributedShufle.forward_shuffle(x2, epoch, cast_dtype=self.amp_dtype,
-                                                                               channels_last=self.nhwc)
+                                                                               channels_last=layout)
             x2.record_stream(self.side)
         if self.nhwc:
-            x1 = crop_to_channels_last_bf16(x1)
+            x1 = crop_to_s2d_bf16(x1) if layout == "s2d" else crop_to_channels_last_bf16(x1)
         with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
             feat_q = self.model(x1)                                                  # train.py:256
         with torch.no_grad():
@@ -134,7 +141,7 @@ class MoCoStep:
                 x2_shuffled.record_stream(main)
             else:
                 x2_shuffled, backward_inds = DistributedShufle.forward_shuffle(x2, epoch, cast_dtype=self.amp_dtype,
-                                                                               channels_last=self.nhwc)
+                                                                               channels_last=layout)
             with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
                 feat_k = self.model_ema(x2_shuffled)                                 # train.py:259
         if self.graph_tail:

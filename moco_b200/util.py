@@ -208,7 +208,7 @@ class ShuffleContext:
         lib = _lib.load()
         _lib.require_cuda(x, src_rows)
         if channels_last:
-            return self._gather_nhwc(kind, x, src_rows)
+            return self._gather_nhwc(kind, x, src_rows, s2d=(channels_last == "s2d"))
         x = x.contiguous()
         n = x.shape[0]
         dtype = cast_dtype if (cast_dtype is not None and self.world > 1) else x.dtype
@@ -228,7 +228,7 @@ class ShuffleContext:
         self._pull(table, n, src_rows, row_bytes, out.data_ptr(), synced=True)
         return out
 
-    def _gather_nhwc(self, kind: str, x: torch.Tensor, src_rows: torch.Tensor) -> torch.Tensor:
+    def _gather_nhwc(self, kind: str, x: torch.Tensor, src_rows: torch.Tensor, s2d: bool = False) -> torch.Tensor:
         lib = _lib.load()
         if x.dim() != 4:
             raise ValueError("moco_b200 shuffle: channels_last needs an [N, C, H, W] batch")
@@ -237,6 +237,23 @@ class ShuffleContext:
         if n and x.stride()[1:] != (H * W, W, 1):          # a channel slice of a wider NCHW batch is read in place
             x = x.contiguous()
         img_stride = x.stride(0) if n else C * H * W
+        if s2d:
+            # channels_last="s2d": the rows that cross NVLink are already in the space-to-depth layout the stem reads
+            _check_s2d_shape(C, H, W)
+            R, Q = H // 2 + 3, W // 2 + 3
+            row_bytes = R * Q * 16 * 2
+            out = torch.empty((src_rows.shape[0], 16, R, Q), dtype=torch.bfloat16, device=x.device,
+                              memory_format=torch.channels_last)
+            if self.world == 1:
+                _lib.check(lib.moco_crop_s2d_bf16(x.data_ptr(), _lib.dtype_code(x), img_stride, src_rows.data_ptr(),
+                                                  out.data_ptr(), src_rows.shape[0], H, W, _lib.cur_stream()),
+                           "moco_crop_s2d_bf16")
+                return out
+            buf = self._staging(kind + "_s2d", n * row_bytes)
+            _lib.check(lib.moco_crop_s2d_bf16(x.data_ptr(), _lib.dtype_code(x), img_stride, None, buf.local, n, H, W,
+                                              _lib.cur_stream()), "moco_crop_s2d_bf16")
+            self._pull(buf.table, n, src_rows, row_bytes, out.data_ptr(), synced=True)
+            return out
         row_bytes = C * H * W * 2
         if row_bytes % 16 != 0:
             raise ValueError(f"moco_b200 shuffle: row size {row_bytes} B is not a multiple of 16")
@@ -258,6 +275,31 @@ class ShuffleContext:
 def _check_nhwc_shape(C: int, H: int, W: int) -> None:
     if C > 4 or (H * W) % 8 != 0:
         raise ValueError(f"moco_b200: the fused bf16/NHWC image path needs C <= 4 and H*W % 8 == 0 (got C={C}, H*W={H * W})")
+
+
+def _check_s2d_shape(C: int, H: int, W: int) -> None:
+    if C != 3 or H % 2 or W % 2:
+        raise ValueError(f"moco_b200: the space-to-depth input path needs 3 channels and even H, W (got {C}, {H}, {W})")
+
+
+def crop_to_s2d_bf16(x: torch.Tensor) -> torch.Tensor:
+    """[N, 3, H, W] fp32/bf16 (possibly one crop of the 6-channel batch, train.py:250) -> bf16 [N, 16, H/2+3, W/2+3]
+    in ``channels_last`` storage: the space-to-depth layout :class:`moco_b200.encoders.StemConv` convolves with a
+    4x4 / stride 1 kernel (``moco_crop_s2d_bf16``)."""
+    lib = _lib.load()
+    _lib.require_cuda(x)
+    if x.dim() != 4:
+        raise ValueError("crop_to_s2d_bf16: expected [N, 3, H, W]")
+    n, C, H, W = x.shape
+    _check_s2d_shape(C, H, W)
+    if n and x.stride()[1:] != (H * W, W, 1):
+        x = x.contiguous()
+    out = torch.empty((n, 16, H // 2 + 3, W // 2 + 3), dtype=torch.bfloat16, device=x.device,
+                      memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.moco_crop_s2d_bf16(x.data_ptr(), _lib.dtype_code(x), x.stride(0) if n else C * H * W, None,
+                                          out.data_ptr(), n, H, W, _lib.cur_stream()), "moco_crop_s2d_bf16")
+    return out
 
 
 def crop_to_channels_last_bf16(x: torch.Tensor) -> torch.Tensor:
@@ -298,7 +340,8 @@ class DistributedShufle:
     def forward_shuffle(x, epoch, cast_dtype=None, channels_last=False):
         """forward shuffle, return shuffled batch of x from all processes (util.py:69-79).
         epoch is used as manual seed to make sure the shuffle id in all process is same.
-        cast_dtype / channels_last: optional extensions, see ShuffleContext.gather."""
+        cast_dtype / channels_last: optional extensions, see ShuffleContext.gather (channels_last="s2d": bf16
+        space-to-depth rows for encoders.StemConv)."""
         rank, world = _world()
         forward_inds, backward_inds = DistributedShufle.get_shuffle_ids(x.shape[0] * world, epoch, x.device)
         forward_inds_local = DistributedShufle.get_local_id(forward_inds)

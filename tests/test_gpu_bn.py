@@ -206,3 +206,56 @@ def test_maxpool3x3s2_matches_torch_bit_exact(N, C, H, W):
     before = L.launches
     assert torch.equal(pool(x.float()), z.detach())
     assert L.launches == before
+
+
+def _s2d_reference(x):
+    """moco_crop_s2d_bf16's layout from torch ops: [N, 3, H, W] -> bf16 [N, 16, H/2+3, W/2+3]."""
+    N, C, H, W = x.shape
+    xp = F.pad(x.to(torch.bfloat16), (4, 2, 4, 2))
+    R, Q = H // 2 + 3, W // 2 + 3
+    xs = xp.view(N, C, R, 2, Q, 2).permute(0, 3, 5, 1, 2, 4).reshape(N, 12, R, Q)
+    return F.pad(xs, (0, 0, 0, 0, 0, 4))
+
+
+@pytest.mark.parametrize("src_dtype", [torch.float32, torch.bfloat16])
+def test_crop_to_s2d_is_the_layout_the_header_defines(src_dtype):
+    from moco_b200.util import DistributedShufle, crop_to_s2d_bf16
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    six = torch.randn(6, 6, 224, 224, device=dev, generator=g).to(src_dtype)
+    crop = six[:, 3:]                                             # a channel slice of the 6-channel batch, read in place
+    out = crop_to_s2d_bf16(crop)
+    assert out.shape == (6, 16, 115, 115) and out.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(out, _s2d_reference(crop))
+    small = torch.randn(3, 3, 10, 6, device=dev, generator=g).to(src_dtype)
+    assert torch.equal(crop_to_s2d_bf16(small), _s2d_reference(small))
+    # single-GPU ShuffleBN: the permutation rides in the same kernel
+    shuf, binds = DistributedShufle.forward_shuffle(crop, 3, cast_dtype=torch.bfloat16, channels_last="s2d")
+    finds, _ = DistributedShufle.get_shuffle_ids(6, 3, dev)
+    assert torch.equal(shuf, _s2d_reference(crop)[finds])
+
+
+def test_stem_conv_on_s2d_input_is_the_7x7_convolution():
+    """moco/models/resnet.py:112 on the plain NHWC crop vs the 4x4 convolution on the space-to-depth crop: same
+    function of the same 7x7 parameter, forward and weight gradient (bf16 autocast, cuDNN both times)."""
+    from moco_b200 import encoders
+    from moco_b200.util import crop_to_channels_last_bf16, crop_to_s2d_bf16
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    stem = encoders.StemConv().to(dev).to(memory_format=torch.channels_last)
+    x = torch.randn(8, 3, 224, 224, device=dev)
+    dy = torch.randn(8, 64, 112, 112, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        a = stem(crop_to_channels_last_bf16(x))
+        b = stem(crop_to_s2d_bf16(x))
+    assert a.shape == b.shape == (8, 64, 112, 112)
+    ref = F.conv2d(x.bfloat16().float(), stem.weight.detach().bfloat16().float(), None, 2, 3)
+    ea = float((a.float() - ref).abs().max())
+    eb = float((b.float() - ref).abs().max())
+    assert eb < max(2 * ea, 0.05), (ea, eb)
+    a.backward(dy)
+    ga = stem.weight.grad.clone()
+    stem.weight.grad = None
+    b.backward(dy)
+    gb = stem.weight.grad
+    assert float((ga - gb).norm() / ga.norm()) < 2e-2

@@ -55,6 +55,16 @@ def correctness(rank, world, dev):
               and np.array_equal(mine.float().cpu().numpy(), outs[rank]))
         res[f"nhwc{it}"] = bool(ok)
         res["ok"] = res["ok"] and bool(ok)
+        # the same crops as space-to-depth rows (what MoCoStep moves when the encoders take them): the oracle's
+        # shuffled bf16 images, re-laid-out with torch ops, must equal the pulled rows bit for bit
+        mine, _ = DistributedShufle.forward_shuffle(six[rank].to(dev)[:, 3:], epoch, channels_last="s2d")
+        want = torch.from_numpy(outs[rank])                                                  # [n, 3, 8, 8] bf16 values
+        xp = torch.nn.functional.pad(want, (4, 2, 4, 2)).view(8, 3, 7, 2, 7, 2).permute(0, 3, 5, 1, 2, 4).reshape(8, 12, 7, 7)
+        want = torch.nn.functional.pad(xp, (0, 0, 0, 0, 0, 4))
+        ok = (mine.shape == (8, 16, 7, 7) and mine.is_contiguous(memory_format=torch.channels_last)
+              and np.array_equal(mine.float().cpu().numpy(), want.numpy()))
+        res[f"nhwc_s2d{it}"] = bool(ok)
+        res["ok"] = res["ok"] and bool(ok)
     col = dist_collect(xs[rank].to(dev))
     ok = np.array_equal(col.cpu().numpy(), O.dist_collect([x.numpy() for x in xs]))
     res["dist_collect"] = bool(ok)
