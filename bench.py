@@ -270,13 +270,11 @@ def shufflebn_block(x2, epoch, rank, world, dev, nhwc):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) * 1e3
 
-    # the rows the step moves: bf16 NHWC crops in the space-to-depth layout of the stem (moco_crop_s2d_bf16) when the
-    # encoders run channels_last, plain bf16 rows otherwise
-    layout = "s2d" if nhwc else False
-    fwd_us = timed_us(lambda: DistributedShufle.forward_shuffle(x2, epoch, cast_dtype=torch.bfloat16, channels_last=layout))
+    # the rows the step moves between GPUs (MoCoStep): the key crops as plain bf16 NHWC rows
+    fwd_us = timed_us(lambda: DistributedShufle.forward_shuffle(x2, epoch, cast_dtype=torch.bfloat16, channels_last=nhwc))
     # the pull alone, on pre-staged data (bf16 rows = what crosses NVLink in the step)
     ctx = ShuffleContext.get()
-    row_bytes = (x2.shape[2] // 2 + 3) * (x2.shape[3] // 2 + 3) * 16 * 2 if nhwc else x2[0].numel() * 2
+    row_bytes = x2[0].numel() * 2
     buf = ctx._staging("bench_fwd", n * row_bytes)
     buf.tensor((n * row_bytes // 2,), torch.bfloat16).normal_()
     ctx.barrier()
@@ -290,7 +288,7 @@ def shufflebn_block(x2, epoch, rank, world, dev, nhwc):
     rr = torch.tensor([float(remote)], device=dev)
     dist.all_reduce(rr, op=dist.ReduceOp.MIN)
     return {"fwd_us": fwd_us, "gather_us": gather_us, "remote_rows": remote, "rows": n, "row_bytes": row_bytes,
-            "row_layout": "bf16 [115, 115, 16] space-to-depth NHWC (12 of 16 channels carry data)" if nhwc else "bf16 NCHW",
+            "row_layout": "bf16 NHWC [224, 224, 3]" if nhwc else "bf16 NCHW",
             "gather_GBps": n * row_bytes / (gather_us * 1e-6) / 1e9,
             "nvlink_GBps": remote * row_bytes / (gather_us * 1e-6) / 1e9,
             "nvlink_frac_of_900": remote * row_bytes / (gather_us * 1e-6) / 1e9 / 900.0,

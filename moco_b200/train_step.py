@@ -124,12 +124,16 @@ class MoCoStep:
         # bf16 NHWC crops; in the space-to-depth layout when both encoders' stems take it and the images allow it
         layout = self.nhwc and ("s2d" if (self.s2d and x1.shape[1] == 3 and x1.shape[2] % 2 == 0 and x1.shape[3] % 2 == 0)
                                 else True)
+        # Key crops that cross NVLink stay plain bf16 NHWC rows (301 KB at 224 x 224): the space-to-depth rows are 423 KB,
+        # a quarter of it zero channels, and measured at 8 GPUs they pull at 517 GB/s (0.57 of the link) against
+        # 547-564 GB/s for the plain rows -- the key encoder's first convolution then runs on 3 channels.
+        layout_k = True if (layout == "s2d" and _world()[1] > 1) else layout
         if self.side is not None:
             # ShuffleBN forward (train.py:258) on the side stream while the query encoder runs
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side), torch.no_grad():
                 x2_shuffled, backward_inds = DistributedShufle.forward_shuffle(x2, epoch, cast_dtype=self.amp_dtype,
-                                                                               channels_last=layout)
+                                                                               channels_last=layout_k)
             x2.record_stream(self.side)
         if self.nhwc:
             x1 = crop_to_s2d_bf16(x1) if layout == "s2d" else crop_to_channels_last_bf16(x1)
@@ -141,7 +145,7 @@ class MoCoStep:
                 x2_shuffled.record_stream(main)
             else:
                 x2_shuffled, backward_inds = DistributedShufle.forward_shuffle(x2, epoch, cast_dtype=self.amp_dtype,
-                                                                               channels_last=layout)
+                                                                               channels_last=layout_k)
             with torch.autocast("cuda", dtype=self.amp_dtype, enabled=self.amp_dtype is not None):
                 feat_k = self.model_ema(x2_shuffled)                                 # train.py:259
         if self.graph_tail:
