@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MOCO_B200_ABI_VERSION 2
+#define MOCO_B200_ABI_VERSION 3 /* 3: + moco_bn_*, moco_maxpool3x3s2_*, moco_crop_s2d_bf16 (additive) */
 
 enum {
     MOCO_OK = 0,

@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_uint3
 
 from . import build as _build
 
-ABI_VERSION = 2                    # MOCO_B200_ABI_VERSION (include/moco_b200.h)
+ABI_VERSION = 3                    # MOCO_B200_ABI_VERSION (include/moco_b200.h)
 MOCO_F32, MOCO_BF16 = 0, 1
 NCE_AUTO, NCE_FORCE_SIMT, NCE_CTA_PAIR, NCE_SINGLE_CTA = 0, 1, 2, 4
 NCE_TWO_PASS, NCE_ONE_PASS = 512, 1024

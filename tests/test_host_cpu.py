@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert ctypes.cast(getattr(raw, n), ctypes.c_void_p).value
         assert callable(getattr(lib, n))
-    assert lib.moco_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.moco_abi_version() == _lib.ABI_VERSION == 3
     assert lib.moco_nce_workspace_bytes(256, 128, 16384) > 0
 
 
