@@ -702,7 +702,7 @@ def test_step_with_fused_input_path_matches_plain_step():
     from moco_b200.NCE import MemoryMoCo
     from moco_b200.train_step import MoCoStep
     losses = []
-    for nhwc in (False, True):
+    for nhwc in (False, "nhwc", True):             # plain; bf16 NHWC crops; bf16 space-to-depth crops (StemConv's 4x4 form)
         torch.manual_seed(0)
         model = encoders.resnet18(low_dim=128).cuda().to(memory_format=torch.channels_last)
         ema = encoders.resnet18(low_dim=128).cuda().to(memory_format=torch.channels_last)
@@ -722,9 +722,14 @@ def test_step_with_fused_input_path_matches_plain_step():
         losses.append(out)
     # identical values enter both encoders; the bound only leaves room for run-to-run cuDNN non-determinism in the
     # two later steps (a wrong crop or layout would move the loss by O(1))
-    for (l0, p0), (l1, p1) in zip(*losses):
+    for (l0, p0), (l1, p1) in zip(losses[0], losses[1]):
         assert abs(l0 - l1) < 1e-2 * max(1.0, abs(l0)), (losses)
         assert abs(p0 - p1) < 5e-2 * max(p0, 1e-6) + 1e-6
+    # space-to-depth crops: the first convolution is the same function but another cuDNN kernel (other summation
+    # order), so its bf16 outputs differ in the last bit and two SGD steps amplify that
+    for (l0, p0), (l2, p2) in zip(losses[0], losses[2]):
+        assert abs(l0 - l2) < 3e-2 * max(1.0, abs(l0)), (losses)
+        assert abs(p0 - p2) < 0.15 * max(p0, 1e-6) + 1e-6
 
 
 @pytest.mark.parametrize("graph", [False, True])
