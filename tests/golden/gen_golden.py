@@ -189,8 +189,72 @@ def gen_ema():
     np.savez_compressed(os.path.join(OUT, "ema.npz"), **out)
 
 
+# ------------------------------------------------------------------ encoder-side ops (BN group, max-pool, conv1)
+def gen_encoder_ops():
+    """Tensors captured INSIDE the reference's own modules (moco/models/resnet.py): the stem
+    (conv1 -> bn1 -> relu -> maxpool, :155-158) and one Bottleneck with a downsample branch (:83-104), forward values
+    and autograd gradients, fp32 on CPU."""
+    from moco.models.resnet import ResNet, Bottleneck
+    import torch.nn as nn
+    out = {}
+    torch.manual_seed(11)
+    net = ResNet(Bottleneck, [1, 1, 1, 1], low_dim=16)
+    net.train()
+    with torch.no_grad():
+        net.bn1.weight.copy_(torch.rand(64) + 0.5)
+        net.bn1.bias.copy_(torch.randn(64) * 0.2)
+    x = torch.randn(4, 3, 32, 32)
+    cap = {}
+
+    def keep(name, clone=False):
+        def hook(m, i, o):                        # returns None: the module's output is left alone
+            o.retain_grad()
+            cap[name] = o
+            if clone:
+                cap[name + "_val"] = o.detach().clone()
+        return hook
+    h1 = net.conv1.register_forward_hook(keep("conv1"))
+    y = net(x, layer=1)                                                   # conv1 -> bn1 -> relu -> maxpool
+    h1.remove()
+    dp = torch.randn_like(y)
+    rm0, rv0 = torch.zeros(64), torch.ones(64)
+    y.backward(dp)
+    out.update(stem_x=x.numpy(), stem_w=net.conv1.weight.detach().numpy(), stem_conv1=cap["conv1"].detach().numpy(),
+               stem_gamma=net.bn1.weight.detach().numpy(), stem_beta=net.bn1.bias.detach().numpy(),
+               stem_pooled=y.detach().numpy(), stem_dpooled=dp.numpy(), stem_dconv1=cap["conv1"].grad.numpy(),
+               stem_dgamma=net.bn1.weight.grad.numpy(), stem_dbeta=net.bn1.bias.grad.numpy(),
+               stem_running_mean=net.bn1.running_mean.numpy().copy(), stem_running_var=net.bn1.running_var.numpy().copy(),
+               stem_running_mean0=rm0.numpy(), stem_running_var0=rv0.numpy())
+    # one Bottleneck whose residual comes from a downsample branch, so that the residual's gradient is observable
+    torch.manual_seed(12)
+    ds = nn.Sequential(nn.Conv2d(32, 64, kernel_size=1, stride=1, bias=False), nn.BatchNorm2d(64))
+    blk = Bottleneck(32, 16, stride=1, downsample=ds)
+    blk.train()
+    with torch.no_grad():
+        blk.bn3.weight.copy_(torch.rand(64) + 0.5)
+        blk.bn3.bias.copy_(torch.randn(64) * 0.2)
+    xb = torch.randn(3, 32, 6, 6)
+    cap.clear()
+    h3 = blk.conv3.register_forward_hook(keep("conv3"))
+    hd = ds.register_forward_hook(keep("res", clone=True))
+    yb = blk(xb)
+    h3.remove(); hd.remove()
+    dyb = torch.randn_like(yb)
+    yb.backward(dyb)
+    out.update(blk_conv3=cap["conv3"].detach().numpy(), blk_res=cap["res_val"].numpy(), blk_gamma=blk.bn3.weight.detach().numpy(),
+               blk_beta=blk.bn3.bias.detach().numpy(), blk_out=yb.detach().numpy(), blk_dout=dyb.numpy(),
+               blk_dconv3=cap["conv3"].grad.numpy(), blk_dres=cap["res"].grad.numpy(),
+               blk_dgamma=blk.bn3.weight.grad.numpy(), blk_dbeta=blk.bn3.bias.grad.numpy(),
+               blk_running_mean=blk.bn3.running_mean.numpy().copy(), blk_running_var=blk.bn3.running_var.numpy().copy())
+    np.savez_compressed(os.path.join(OUT, "encoder_ops.npz"), **out)
+
+
 if __name__ == "__main__":
     _shim()
+    if "--only-encoder-ops" in sys.argv:
+        gen_encoder_ops()
+        sys.exit(0)
+    gen_encoder_ops()
     gen_ema()
     gen_shuffle_ids()
     gen_contrast()

@@ -4,6 +4,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 from oracle import moco_oracle as O
 
@@ -170,3 +171,90 @@ def test_normalize_head_matches_reference(golden_dir):
         # the kernels' operand contract (bf16 q^ for the negatives) stays within the bf16 quantisation of the logits
         l2, p2, d2, _, _ = O.head_with_normalize(g[f"{name}_xq"], g[f"{name}_xk"], g[f"{name}_memory0"], T, True)
         assert abs(l2 - loss) < 5e-3 and np.abs(d2 - dxq).max() / np.abs(dxq).max() < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# encoder-side ops (BatchNorm group, stem max-pool, space-to-depth conv1): oracle/encoder_ops_oracle.py against tensors
+# captured inside the reference's own ResNet / Bottleneck modules (tests/golden/gen_golden.py:gen_encoder_ops)
+# ---------------------------------------------------------------------------------------------------------------------
+def _enc(golden_dir):
+    return np.load(os.path.join(golden_dir, "encoder_ops.npz"))
+
+
+def _close(a, b, rtol=2e-5, atol=2e-5):
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol * max(1.0, float(np.abs(b).max())))
+
+
+def test_encoder_oracle_stem_bn_relu_maxpool_matches_reference_modules(golden_dir):
+    """resnet.py:155-158: conv1 output -> bn1 -> relu -> maxpool, forward and autograd."""
+    from oracle import encoder_ops_oracle as E
+    g = _enc(golden_dir)
+    x = g["stem_conv1"]
+    y, mean, invstd = E.bn_act_forward(x, g["stem_gamma"], g["stem_beta"], None, True)
+    pooled, taps = E.maxpool3x3s2_forward(y)
+    _close(pooled, g["stem_pooled"])
+    dy = E.maxpool3x3s2_backward(g["stem_dpooled"], taps, y.shape)
+    dx, dgamma, dbeta, dres = E.bn_act_backward(x, g["stem_gamma"], g["stem_beta"], dy, None, True)
+    assert dres is None
+    _close(dx, g["stem_dconv1"], 2e-4, 2e-5)
+    _close(dgamma, g["stem_dgamma"], 2e-4, 2e-5)
+    _close(dbeta, g["stem_dbeta"], 2e-4, 2e-5)
+    mean_, var_ = E.batchnorm_stats(x)
+    rm, rv = E.running_stats_update(g["stem_running_mean0"], g["stem_running_var0"], mean_, var_,
+                                    x.shape[0] * x.shape[2] * x.shape[3])
+    _close(rm, g["stem_running_mean"])
+    _close(rv, g["stem_running_var"])
+
+
+def test_encoder_oracle_bn_add_relu_matches_reference_bottleneck(golden_dir):
+    """resnet.py:95-102: conv3 output -> bn3 -> += residual -> relu, incl. the gradient that reaches the residual."""
+    from oracle import encoder_ops_oracle as E
+    g = _enc(golden_dir)
+    x, res = g["blk_conv3"], g["blk_res"]
+    y, _, _ = E.bn_act_forward(x, g["blk_gamma"], g["blk_beta"], res, True)
+    _close(y, g["blk_out"])
+    dx, dgamma, dbeta, dres = E.bn_act_backward(x, g["blk_gamma"], g["blk_beta"], g["blk_dout"], res, True)
+    _close(dx, g["blk_dconv3"], 2e-4, 2e-5)
+    _close(dres, g["blk_dres"])
+    _close(dgamma, g["blk_dgamma"], 2e-4, 2e-5)
+    _close(dbeta, g["blk_dbeta"], 2e-4, 2e-5)
+
+
+def test_space_to_depth_stem_is_the_reference_conv1(golden_dir):
+    """resnet.py:112,155: the 7x7 / 2 / pad 3 convolution the reference ran == the 4x4 / 1 / pad 0 convolution over the
+    space-to-depth layout with the re-indexed weights -- oracle restatement, and moco_b200.encoders.StemConv on CPU."""
+    from oracle import encoder_ops_oracle as E
+    g = _enc(golden_dir)
+    xs, ws = E.s2d_layout(g["stem_x"]), E.stem_weight_s2d(g["stem_w"])
+    assert xs.shape == (4, 16, 19, 19) and ws.shape == (64, 16, 4, 4)
+    _close(E.conv2d_valid(xs, ws), g["stem_conv1"], 2e-5, 2e-5)
+    from moco_b200.encoders import StemConv
+    stem = StemConv()
+    with torch.no_grad():
+        stem.weight.copy_(torch.from_numpy(g["stem_w"]))
+        np.testing.assert_array_equal(stem.s2d_weight().numpy(), ws)
+        _close(stem(torch.from_numpy(xs)).numpy(), g["stem_conv1"], 2e-5, 2e-5)
+        _close(stem(torch.from_numpy(g["stem_x"])).numpy(), g["stem_conv1"], 2e-5, 2e-5)
+
+
+def test_norm_modules_off_the_gpu_reproduce_the_reference_modules(golden_dir):
+    """BatchNormAct2d / MaxPool3x3s2 on CPU tensors (their torch path) against the same captured tensors."""
+    from moco_b200.bn import BatchNormAct2d, MaxPool3x3s2
+    g = _enc(golden_dir)
+    bn = BatchNormAct2d(64, relu=True)
+    with torch.no_grad():
+        bn.weight.copy_(torch.from_numpy(g["blk_gamma"]))
+        bn.bias.copy_(torch.from_numpy(g["blk_beta"]))
+    x = torch.from_numpy(g["blk_conv3"]).requires_grad_(True)
+    res = torch.from_numpy(g["blk_res"]).requires_grad_(True)
+    y = bn(x, res)
+    y.backward(torch.from_numpy(g["blk_dout"]))
+    _close(y.detach().numpy(), g["blk_out"])
+    _close(x.grad.numpy(), g["blk_dconv3"], 2e-5, 2e-5)
+    _close(res.grad.numpy(), g["blk_dres"])
+    _close(bn.running_var.numpy(), g["blk_running_var"])
+    stem_bn = BatchNormAct2d(64, relu=True)
+    with torch.no_grad():
+        stem_bn.weight.copy_(torch.from_numpy(g["stem_gamma"]))
+        stem_bn.bias.copy_(torch.from_numpy(g["stem_beta"]))
+    _close(MaxPool3x3s2()(stem_bn(torch.from_numpy(g["stem_conv1"]))).detach().numpy(), g["stem_pooled"])
