@@ -8,7 +8,10 @@ Differences from the reference loop body, none of which change the math:
 * encoders run under bf16 autocast in channels_last (the reference used Apex AMP, train.py:189-196);
 * with ``channels_last=True`` the two crops are taken straight from the 6-channel batch (train.py:250-254) as
   bf16 NHWC by one kernel each (x1: ``crop_to_channels_last_bf16``; x2: inside the ShuffleBN publish), which is
-  what autocast + cuDNN would have produced with two more passes over the images;
+  what autocast + cuDNN would have produced with two more passes over the images; when the encoders' stem takes it
+  (``encoders.StemConv``) the crops are written in the space-to-depth layout instead (``crop_to_s2d_bf16``), in which
+  the 7x7 first convolution is a 16-channel 4x4 one -- for both crops on one GPU, for the query crop only when the
+  key crops have to cross NVLink (``channels_last="nhwc"`` keeps the plain NHWC crops everywhere);
 * ``fuse_normalize=True``: the encoders return their raw ``fc`` output and the L2 normalisation of
   ``moco/models/resnet.py:24-33`` -- forward for q, k and the enqueued keys, backward for q -- happens inside the
   head's two kernels instead of ~14 elementwise launches around them;
